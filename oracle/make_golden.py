@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (CPU, shims) on seeded
+synthetic inputs.  Run in the build container only:  python -m oracle.make_golden
+
+TEST INFRASTRUCTURE ONLY.  The reference has no golden vectors of its own (SURVEY.md
+section 4), so these files *are* the pin: outputs of the reference code itself
+(/root/reference/code @ a5399816) on inputs that mvsdf_b200/synth.py regenerates
+bit-identically from seeds.  Weights are not stored; each file carries the sha256 prefix
+of the state_dict it was produced with and tests refuse to run on a mismatch.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from mvsdf_b200 import synth  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> (width, weight kwargs)
+WEIGHT_PRESETS = {
+    "w256": dict(width=256, seed=1, perturb=0.05, pe_noise=0.003, bias=0.6),
+    "w256_geo": dict(width=256, seed=1, perturb=0.0, pe_noise=0.0, bias=0.6),
+    "w512": dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75),
+}
+
+
+def build_reference_model(ref, preset: str):
+    kw = WEIGHT_PRESETS[preset]
+    sd = synth.make_state_dict(**kw)
+    model = ref.idr.IDRNetwork(ref_shim.DictConf(ref_shim.model_conf(kw["width"])))
+    missing = model.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model, sd
+
+
+def npify(d):
+    out = {}
+    for k, v in d.items():
+        if v is None:
+            continue
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    return out
+
+
+class UniformLog:
+    """Records the CPU-generator draws the reference makes inside forward (fact 0.10)."""
+
+    def __enter__(self):
+        self.draws = []
+        self._orig = torch.Tensor.uniform_
+
+        def logged(t, *a, **k):
+            r = self._orig(t, *a, **k)
+            self.draws.append(r.clone())
+            return r
+
+        torch.Tensor.uniform_ = logged
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.uniform_ = self._orig
+
+
+def case_forward(ref, name, preset, H, W, n_images, n_src, n_rays, training, tp, seed, mask_mode="ones"):
+    model, sd = build_reference_model(ref, preset)
+    scene = synth.make_scene(H, W, n_images=n_images, n_src=n_src, n_rays=n_rays, seed=seed, mask_mode=mask_mode)
+    model.train(training)
+    inp = {k: scene[k].clone() for k in ["uv", "pose", "intrinsics", "object_mask"]}
+    torch.manual_seed(4321 + seed)
+    with ref_shim.quiet(), UniformLog() as log:
+        out = model(inp, tp)
+    loss_mod = ref.loss.IDRLoss()
+    nm, om = out["network_object_mask"], out["object_mask"]
+    with ref_shim.quiet():
+        rgb_l = loss_mod.get_rgb_loss(out["rgb_values"], scene["rgb"], nm, om)
+        feat_l = loss_mod.get_feat_loss_corr(out["diff_surf_pts"], None, scene["feat"], scene["cam"],
+                                             scene["feat_src"], scene["src_cams"], scene["size"][:1],
+                                             scene["center"][:1], nm, om)
+    res = {
+        "meta_preset": preset, "meta_weights_sha": synth.state_dict_checksum(sd),
+        "meta_scene": np.array([H, W, n_images, n_src, -1 if n_rays is None else n_rays, seed]),
+        "meta_mask_mode": mask_mode, "meta_training": int(training), "meta_tp": -1.0 if tp is None else tp,
+        "points": out["points"], "dists": (out["points"] - scene["pose"][:, :3, 3].unsqueeze(1).repeat(
+            1, scene["uv"].shape[1], 1).reshape(-1, 3)).norm(dim=1),
+        "network_object_mask": nm, "rgb_values": out["rgb_values"], "sdf_output": out["sdf_output"],
+        "diff_surf_pts": out["diff_surf_pts"], "rgb_loss": rgb_l, "feat_loss": feat_l,
+    }
+    if training:
+        with ref_shim.quiet():
+            res["eikonal_loss"] = loss_mod.get_eikonal_loss(out["grad_theta"])
+            res["surf_loss"] = loss_mod.get_surf_loss(out["surf_indicator_output"], nm, out["object_mask_true"])
+        res["grad_theta"] = out["grad_theta"]
+        res["eikonal_output"] = out["eikonal_output"]
+        res["surf_indicator_output"] = out["surf_indicator_output"]
+        draws = log.draws
+        # order of draws: [min-sdf steps (100) if that stage ran], eikonal points (n_eik x 3)
+        if len(draws) == 2:
+            res["steps01"] = draws[0]
+            res["eik_points"] = draws[1]
+        else:
+            assert len(draws) == 1
+            res["eik_points"] = draws[0]
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **npify(res))
+    print(f"{name}: hits {int(nm.sum())}/{nm.numel()}  rgb_loss {float(rgb_l):.6f}  feat_loss {float(feat_l):.6f}")
+
+
+def case_mlp(ref, name, preset, n_pts, seed):
+    model, sd = build_reference_model(ref, preset)
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n_pts, 3, generator=g) * 2 - 1) * 0.9
+    model.train()
+    full = model.implicit_network(x)
+    grad = model.implicit_network.gradient(x.clone())[:, 0, :]
+    view = torch.nn.functional.normalize(torch.randn(n_pts, 3, generator=g), dim=1)
+    rgb = model.rendering_network(x, grad.detach(), view, full[:, 2:].detach())
+    res = {
+        "meta_preset": preset, "meta_weights_sha": synth.state_dict_checksum(sd),
+        "x": x, "view": view, "sdf_full": full, "grad": grad, "rgb": rgb,
+    }
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **npify(res))
+    print(f"{name}: sdf range {float(full[:, 0].min()):.3f}..{float(full[:, 0].max()):.3f}")
+
+
+def case_tracer(ref, name, preset, H, W, n_images, training, seed):
+    """RayTracing.forward alone (row a6) incl. the intermediate ray set-up (rows a1, a2)."""
+    model, sd = build_reference_model(ref, preset)
+    scene = synth.make_scene(H, W, n_images=n_images, n_src=1, seed=seed)
+    dirs, cam_loc = ref.rend_util.get_camera_params(scene["uv"], scene["pose"], scene["intrinsics"])
+    t_nf, hit = ref.rend_util.get_sphere_intersection(cam_loc, dirs, r=1.0)
+    model.ray_tracer.train(training)
+    model.implicit_network.eval()
+    torch.manual_seed(99 + seed)
+    with torch.no_grad(), ref_shim.quiet(), UniformLog() as log:
+        pts, nm, dists = model.ray_tracer(sdf=lambda x: model.implicit_network(x)[:, 0], cam_loc=cam_loc,
+                                          object_mask=scene["object_mask"].reshape(-1), ray_directions=dirs)
+    res = {
+        "meta_preset": preset, "meta_weights_sha": synth.state_dict_checksum(sd),
+        "meta_scene": np.array([H, W, n_images, 1, -1, seed]), "meta_training": int(training),
+        "ray_dirs": dirs, "cam_loc": cam_loc, "t_near_far": t_nf, "hit_sphere": hit,
+        "points": pts, "network_object_mask": nm, "dists": dists,
+    }
+    if log.draws:
+        res["steps01"] = log.draws[0]
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **npify(res))
+    print(f"{name}: hits {int(nm.sum())}/{nm.numel()}")
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    ref = ref_shim.load()
+    torch.set_num_threads(8)
+    case_mlp(ref, "mlp_w256", "w256", 192, seed=11)
+    case_mlp(ref, "mlp_w512", "w512", 128, seed=12)
+    case_tracer(ref, "tracer_eval_w256", "w256", 32, 32, 1, False, seed=0)
+    case_tracer(ref, "tracer_train_w256", "w256", 24, 24, 2, True, seed=1)
+    case_tracer(ref, "tracer_eval_w256_geo", "w256_geo", 24, 24, 1, False, seed=2)
+    # BASELINE.json configs[0]: 32x32 rays, 8x256 SDF MLP, 1 source view
+    case_forward(ref, "cfg1_eval_w256", "w256", 32, 32, 1, 1, None, False, None, seed=0)
+    case_forward(ref, "cfg1_train_w256", "w256", 32, 32, 2, 1, 512, True, 0.5, seed=0, mask_mode="disc")
+    case_forward(ref, "small_eval_w512", "w512", 20, 20, 1, 2, None, False, None, seed=3)
+
+
+if __name__ == "__main__":
+    main()

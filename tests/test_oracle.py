@@ -1,0 +1,114 @@
+"""Pins oracle/mvsdf_oracle.py (the CPU restatement) against (a) the golden outputs of the
+unmodified reference (tests/golden, everywhere) and (b) the live reference when
+/root/reference is present (build container only)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvsdf_oracle as O
+from oracle import ref_shim
+from tests.helpers import preset_state_dict, rel_err, scene_from_meta, t
+
+torch.set_num_threads(4)
+
+
+@pytest.mark.parametrize("name", ["mlp_w256", "mlp_w512"])
+def test_mlp_golden(golden, name):
+    g = golden(name)
+    sd = preset_state_dict(str(g["meta_preset"]), g["meta_weights_sha"])
+    sw, rw = O.sdf_weights(sd), O.render_weights(sd)
+    x = t(g["x"])
+    full = O.sdf_mlp(x, sw)
+    assert torch.allclose(full, t(g["sdf_full"]), rtol=1e-5, atol=2e-6)
+    grad = O.sdf_gradient(x, sw)
+    assert torch.allclose(grad, t(g["grad"]), rtol=1e-4, atol=2e-6)
+    rgb = O.render_mlp(x, t(g["grad"]), t(g["view"]), t(g["sdf_full"])[:, 2:], rw)
+    assert torch.allclose(rgb, t(g["rgb"]), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["tracer_eval_w256", "tracer_train_w256", "tracer_eval_w256_geo"])
+def test_tracer_golden(golden, name):
+    g = golden(name)
+    sd = preset_state_dict(str(g["meta_preset"]), g["meta_weights_sha"])
+    sw = O.sdf_weights(sd)
+    scene = scene_from_meta(g)
+    dirs, cam = O.camera_rays(scene["uv"], scene["pose"], scene["intrinsics"])
+    assert torch.allclose(dirs, t(g["ray_dirs"]), atol=1e-6)
+    tnf, hit = O.sphere_intersection(cam, dirs)
+    assert torch.equal(hit, t(g["hit_sphere"]))
+    assert torch.allclose(tnf, t(g["t_near_far"]), atol=1e-5)
+    training = bool(int(g["meta_training"]))
+    steps = t(g["steps01"]) if "steps01" in g else None
+    cnt = O.TraceCounters()
+    with torch.no_grad():
+        pts, nm, dists = O.trace_rays(lambda x: O.sdf_mlp(x, sw)[:, 0], cam, scene["object_mask"].reshape(-1),
+                                      dirs, training=training, steps01=steps, counters=cnt)
+    ref_nm = t(g["network_object_mask"])
+    assert int((nm != ref_nm).sum()) == 0
+    assert torch.allclose(dists, t(g["dists"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(pts, t(g["points"]), rtol=1e-5, atol=1e-5)
+    assert cnt.total > 0
+
+
+@pytest.mark.parametrize("name", ["cfg1_eval_w256", "cfg1_train_w256", "small_eval_w512"])
+def test_forward_golden(golden, name):
+    g = golden(name)
+    sd = preset_state_dict(str(g["meta_preset"]), g["meta_weights_sha"])
+    sw, rw = O.sdf_weights(sd), O.render_weights(sd)
+    scene = scene_from_meta(g)
+    training = bool(int(g["meta_training"]))
+    tp = float(g["meta_tp"]) if float(g["meta_tp"]) >= 0 else None
+    kw = {}
+    if training:
+        kw = dict(steps01=t(g["steps01"]) if "steps01" in g else None, eik_points=t(g["eik_points"]))
+    out = O.idr_forward(sw, rw, scene, tp, training, **kw)
+    nm = out["network_object_mask"]
+    assert torch.equal(nm, t(g["network_object_mask"]))
+    assert torch.allclose(out["points"], t(g["points"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(out["rgb_values"], t(g["rgb_values"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["sdf_output"], t(g["sdf_output"]), rtol=1e-4, atol=2e-6)
+    assert torch.allclose(out["diff_surf_pts"], t(g["diff_surf_pts"]), rtol=1e-5, atol=1e-5)
+    losses = O.hot_path_losses(out, scene, 0.5 if tp is None else tp)
+    assert rel_err(losses["rgb_loss"], g["rgb_loss"]) < 1e-5
+    assert rel_err(losses["feat_loss"], g["feat_loss"]) < 1e-4
+    if training:
+        assert torch.allclose(out["grad_theta"], t(g["grad_theta"]), rtol=1e-4, atol=1e-5)
+        assert rel_err(losses["eikonal_loss"], g["eikonal_loss"]) < 1e-4
+        assert rel_err(losses["surf_loss"], g["surf_loss"]) < 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+def test_live_reference_train_step_matches_oracle():
+    """Runs the unmodified reference and the restatement side by side on a fresh seed,
+    including gradients of the hot-path losses w.r.t. the parameters."""
+    ref = ref_shim.load()
+    from mvsdf_b200 import synth
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    model = ref.idr.IDRNetwork(ref_shim.DictConf(ref_shim.model_conf(64)))
+    model.load_state_dict(sd)
+    scene = synth.make_scene(16, 16, n_images=2, n_src=2, n_rays=128, seed=9)
+    model.train()
+    torch.manual_seed(7)
+    with ref_shim.quiet():
+        r = model({k: scene[k].clone() for k in ["uv", "pose", "intrinsics", "object_mask"]}, 0.3)
+        lm = ref.loss.IDRLoss()
+        r_feat = lm.get_feat_loss_corr(r["diff_surf_pts"], None, scene["feat"], scene["cam"], scene["feat_src"],
+                                       scene["src_cams"], scene["size"][:1], scene["center"][:1],
+                                       r["network_object_mask"], r["object_mask"])
+        r_rgb = lm.get_rgb_loss(r["rgb_values"], scene["rgb"], r["network_object_mask"], r["object_mask"])
+        r_eik = lm.get_eikonal_loss(r["grad_theta"])
+    (r_rgb + r_feat + r_eik).backward()
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    sw, rw = O.sdf_weights(params), O.render_weights(params)
+    torch.manual_seed(7)
+    o = O.idr_forward(sw, rw, scene, 0.3, True)
+    losses = O.hot_path_losses(o, scene, 0.3)
+    assert torch.equal(o["network_object_mask"], r["network_object_mask"])
+    assert rel_err(losses["rgb_loss"], r_rgb) < 1e-5
+    assert rel_err(losses["feat_loss"], r_feat) < 1e-5
+    assert rel_err(losses["eikonal_loss"], r_eik) < 1e-5
+    (losses["rgb_loss"] + losses["feat_loss"] + losses["eikonal_loss"]).backward()
+    for k, gr in ref_grads.items():
+        assert torch.allclose(params[k].grad, gr, rtol=1e-3, atol=1e-6), k
