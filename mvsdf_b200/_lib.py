@@ -1,0 +1,95 @@
+"""ctypes binding of libmvsdf_b200.so (the C ABI declared in include/mvsdf_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails the
+error is raised -- the product path never routes through PyTorch ops or the oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvsdf_b200.so")
+
+_lib = None
+
+
+class MvsdfError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    P = c_void_p
+    lib.mvsdf_abi_version.restype = c_int
+    lib.mvsdf_last_error.restype = c_char_p
+    lib.mvsdf_sdf_net_create.restype = P
+    lib.mvsdf_sdf_net_create.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.mvsdf_render_net_create.restype = P
+    lib.mvsdf_render_net_create.argtypes = [c_int, c_int, c_int, c_int]
+    lib.mvsdf_net_destroy.restype = None
+    lib.mvsdf_net_destroy.argtypes = [P]
+    lib.mvsdf_net_num_layers.restype = c_int
+    lib.mvsdf_net_num_layers.argtypes = [P]
+    lib.mvsdf_net_packed_bytes.restype = c_size_t
+    lib.mvsdf_net_packed_bytes.argtypes = [P]
+    lib.mvsdf_pack_weights.restype = c_int
+    lib.mvsdf_pack_weights.argtypes = [P, POINTER(P), POINTER(P), POINTER(P), P, P]
+    lib.mvsdf_sdf_forward.restype = c_int
+    lib.mvsdf_sdf_forward.argtypes = [P, P, P, c_int64, P, c_int, P, P, P]
+    lib.mvsdf_sdf_value_grad.restype = c_int
+    lib.mvsdf_sdf_value_grad.argtypes = [P, P, P, c_int64, P, c_int, P, P, P, P]
+    lib.mvsdf_render_forward.restype = c_int
+    lib.mvsdf_render_forward.argtypes = [P, P, P, P, P, P, c_int64, P, P, P]
+    # part 2 (tracer / shading / losses) is declared when present
+    if hasattr(lib, "mvsdf_trace_workspace_bytes"):
+        lib.mvsdf_trace_workspace_bytes.restype = c_size_t
+        lib.mvsdf_trace_workspace_bytes.argtypes = [c_int64, c_int]
+        lib.mvsdf_trace.restype = c_int
+        lib.mvsdf_trace.argtypes = [P, P, P, P, P, P, P, c_int, c_int, c_int, P, P, c_size_t, P, P, P, P, P, P, P]
+    if hasattr(lib, "mvsdf_render_rays_workspace_bytes"):
+        lib.mvsdf_render_rays_workspace_bytes.restype = c_size_t
+        lib.mvsdf_render_rays_workspace_bytes.argtypes = [c_int64]
+        lib.mvsdf_render_rays.restype = c_int
+        lib.mvsdf_render_rays.argtypes = [P, P, P, P, P, P, P, P, c_int64, P, c_size_t, P, P, P, P, P, P, P]
+    if hasattr(lib, "mvsdf_feat_nchw_to_nhwc"):
+        lib.mvsdf_feat_nchw_to_nhwc.restype = c_int
+        lib.mvsdf_feat_nchw_to_nhwc.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
+        lib.mvsdf_feat_loss_corr.restype = c_int
+        lib.mvsdf_feat_loss_corr.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
+        lib.mvsdf_rgb_l1.restype = c_int
+        lib.mvsdf_rgb_l1.argtypes = [P, P, P, P, c_int64, P, P]
+    return lib
+
+
+def lib():
+    """Loads the shared library (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MvsdfError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). mvsdf_b200 has no CPU / PyTorch fallback.")
+        _lib = _declare(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().mvsdf_last_error()
+        raise MvsdfError(f"mvsdf_b200 call failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None as c_void_p."""
+    if t is None:
+        return c_void_p(0)
+    assert t.is_contiguous(), "mvsdf_b200 needs contiguous buffers"
+    return c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

@@ -1,0 +1,22 @@
+// Internal (non-ABI) declarations shared by the translation units of libmvsdf_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+
+struct mvsdf_net;
+
+namespace mvsdf {
+
+int fail(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int sm_count();
+
+// MLP tile launches (mlp_abi.cu)
+int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,
+            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st);
+int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const float* view, const float* normals,
+               const float* feats, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st);
+
+}  // namespace mvsdf

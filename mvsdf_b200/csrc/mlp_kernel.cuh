@@ -1,0 +1,391 @@
+// Fused MLP tile core for sm_100a: one persistent CTA per SM pushes tiles of 64 columns
+// (64 points, or 16 points x [value, d/dx, d/dy, d/dz]) through every layer of a weight-norm
+// MLP without the activations ever leaving the SM.
+//
+//   D[feature (TMEM lane), column] (+)= W_tile[feature, k] * X[column, k]        tcgen05.mma, M=128 N=64 K=16
+//
+//   * weights: streamed from L2 as pre-tiled fp16 hi/lo pairs by 1-D bulk async copies (TMA engine)
+//     through a 4-stage mbarrier ring (warp 8);
+//   * activations: resident in shared memory as fp16 hi/lo pairs (K-major, un-swizzled core matrices,
+//     padded K-core stride so the epilogue's 2-byte stores are bank-conflict free);
+//   * 3 UMMAs per K step (hi*hi + lo*hi + hi*lo) give ~22-bit operands with fp32 accumulation in
+//     TMEM -- the reference's fp32 SGEMM accuracy (SURVEY.md fact 0.9 rules out plain TF32/BF16);
+//   * epilogue (warps 0-7): TMEM -> registers -> bias + softplus(beta=100)/ReLU -> fp16 split ->
+//     shared memory, which is the next layer's B operand; forward-mode tangents ride along as
+//     extra columns (value+gradient mode) and are scaled by sigmoid(100 z).
+//
+// Replaces, per call, the reference's embedder + 9 SGEMMs + softplus kernels
+// (model/embedder.py:35, model/implicit_differentiable_renderer.py:77-94) and, in value+gradient mode,
+// the autograd pass of ImplicitNetwork.gradient (:96-107); with NET_RENDER it is
+// RenderingNetwork.forward (:145-167).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "netplan.h"
+#include "ptx.cuh"
+
+namespace mvsdf {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMlpThreads = kEpiThreads + 64;   // + producer warp + MMA warp
+constexpr int kPeCores = 8;                     // PE tile: K padded to 64
+constexpr int kPeTileBytes = kPeCores * kBCoreStride;
+constexpr int kScratchStride = 40;              // floats per point in the prologue scratch
+
+struct MlpArgs {
+  const uint8_t* packed;
+  const float* bias;
+  int n_run;                 // layers to run: hidden layers + one head
+  int skip_layer;
+  int skip_rows_begin;
+  int pe_dim;
+  int k_cores_max;
+  int head;                  // HeadKind
+  int feat_size;
+  long long n;               // number of points (ignored when n_ptr != nullptr)
+  const int* n_ptr;          // optional device-side count
+  const float* x;            // [n,3]
+  const float* view;         // render: [n,3]
+  const float* normals;      // render: [n,3]
+  const float* feats;        // render: [n,feat_size]
+  float* out_sdf;            // [n]            (optional with HEAD_FULL)
+  float* out_full;           // [n, 2+feat]    (HEAD_FULL)
+  float* out_grad;           // [n,3]          (value+gradient mode)
+  float* out_rgb;            // [n,3]          (render)
+  LayerPlan L[10];
+};
+
+__host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
+  return (size_t)kStages * kStageBytes + 2 * (size_t)k_cores_max * kBCoreStride + 2 * kPeTileBytes + 128;
+}
+
+// byte offset of (column n, feature k) inside an activation operand buffer
+__device__ __forceinline__ uint32_t xoff(int n, int k) {
+  return (uint32_t)((k >> 3) * kBCoreStride + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, float v) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  ptx::st_shared_u16(hi_addr, __half_as_ushort(h));
+  ptx::st_shared_u16(lo_addr, __half_as_ushort(l));
+}
+
+// softplus(beta=100, threshold=20) as torch computes it: z if 100 z > 20 else log1p(exp(100 z))/100
+// (nn.Softplus(beta=100), implicit_differentiable_renderer.py:75). Also returns d/dz = sigmoid(100 z).
+__device__ __forceinline__ float softplus100(float z, float& sig) {
+  const float t = z * 100.0f;
+  const float e = ptx::ex2_approx(fminf(t, 20.0f) * 1.4426950408889634f);
+  const float ope = 1.0f + e;
+  const float y = ptx::lg2_approx(ope) * (0.6931471805599453f * 0.01f);
+  sig = t > 20.0f ? 1.0f : e * ptx::rcp_approx(ope);
+  return t > 20.0f ? z : y;
+}
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t xbytes = (uint32_t)a.k_cores_max * kBCoreStride;
+  const uint32_t s_stage = ptx::smem_u32(smem);
+  const uint32_t s_xhi = s_stage + kStages * kStageBytes;
+  const uint32_t s_xlo = s_xhi + xbytes;
+  const uint32_t s_pehi = s_xlo + xbytes;
+  const uint32_t s_pelo = s_pehi + kPeTileBytes;
+  const uint32_t s_bar = s_pelo + kPeTileBytes;          // 16-byte aligned by construction
+  const uint32_t bar_full = s_bar;                       // kStages x 8 B
+  const uint32_t bar_empty = s_bar + 8 * kStages;
+  const uint32_t bar_acc = s_bar + 16 * kStages;         // MMA -> epilogue: layer accumulators complete
+  const uint32_t bar_act = bar_acc + 8;                  // epilogue -> MMA: next B operand ready, TMEM drained
+  const uint32_t s_tmem = bar_act + 8;
+  uint8_t* const g_scratch = (KIND == NET_SDF) ? (smem + kStages * kStageBytes)
+                                               : (smem + kStages * kStageBytes + 2 * xbytes);
+  float* const scratch = reinterpret_cast<float*>(g_scratch);
+
+  const long long n_pts = a.n_ptr ? (long long)(*a.n_ptr) : a.n;
+  constexpr int kPtsPerTile = (MODE == 0) ? kTileN : kTileN / 4;
+  const long long n_tiles = (n_pts + kPtsPerTile - 1) / kPtsPerTile;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_acc, 1);
+    ptx::mbar_init(bar_act, kEpiWarps);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kEpiWarps + 1) {
+    ptx::tmem_alloc(s_tmem, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - s_stage));
+
+  if (warp == kEpiWarps) {
+    // ------------------------------------------------------------------ weight producer
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < a.n_run; ++l) {
+        const LayerPlan& lp = a.L[l];
+        const uint8_t* src = a.packed + lp.w_off;
+        const int n_stage = lp.m_tiles * lp.k_chunks;
+        for (int i = 0; i < n_stage; ++i, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
+            ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)i * kStageBytes, kStageBytes, bar_full + 8 * s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ------------------------------------------------------------------ UMMA issuer
+    constexpr uint32_t idesc = ptx::idesc_f16_f32(kTileM, kTileN);
+    uint32_t it = 0, act_ctr = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < a.n_run; ++l) {
+        const LayerPlan& lp = a.L[l];
+        ptx::mbar_wait(bar_act, act_ctr & 1);
+        ++act_ctr;
+        ptx::tc_fence_after();
+        const uint32_t b_hi = lp.b_from_pe ? s_pehi : s_xhi;
+        const uint32_t b_lo = lp.b_from_pe ? s_pelo : s_xlo;
+        for (int m = 0; m < lp.m_tiles; ++m) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(m * kTileN);
+          for (int kc = 0; kc < lp.k_chunks; ++kc, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            ptx::mbar_wait(bar_full + 8 * s, ph);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_hi = s_stage + s * kStageBytes;
+              const uint32_t a_lo = a_hi + kTileBytes;
+#pragma unroll
+              for (int ks = 0; ks < kChunkK / 16; ++ks) {
+                const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 256, 128, 512);
+                const uint64_t da_lo = ptx::smem_desc(a_lo + ks * 256, 128, 512);
+                const uint32_t boff = (uint32_t)((kc * (kChunkK / 8) + ks * 2) * kBCoreStride);
+                const uint64_t db_hi = ptx::smem_desc(b_hi + boff, kBCoreStride, 128);
+                const uint64_t db_lo = ptx::smem_desc(b_lo + boff, kBCoreStride, 128);
+                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+                ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+              }
+              ptx::umma_commit(bar_empty + 8 * s);   // frees the stage once these UMMAs have read it
+            }
+            __syncwarp();
+          }
+        }
+        if (lane == 0) ptx::umma_commit(bar_acc);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ prologue + epilogue warps
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int h = warp >> 2;             // column half
+    const int row = q * 32 + lane;       // row inside a 128-row output tile
+    const int t = threadIdx.x;           // 0..255
+    constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
+    uint32_t acc_ctr = 0;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long p0 = tile * kPtsPerTile;
+
+      // ---------------- prologue: build the first layer's B operand
+      if (KIND == NET_SDF) {
+        // phase A: positional encoding (model/embedder.py:5-50) of 64 (16) points, one (point, coordinate) per thread
+        if (t < 3 * kPtsPerTile) {
+          const int pt = t / 3, c = t - 3 * pt;
+          const long long gp = p0 + pt;
+          const float xc = gp < n_pts ? __ldg(a.x + gp * 3 + c) : 0.0f;
+          float* pe = scratch + pt * kScratchStride;
+          pe[c] = xc;
+          float* dpe = scratch + (kPtsPerTile + pt) * kScratchStride;
+          if (MODE == 1) dpe[c] = 1.0f;
+          float f = 1.0f;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            float sn, cs;
+            sincosf(xc * f, &sn, &cs);
+            pe[3 + 6 * i + c] = sn;
+            pe[6 + 6 * i + c] = cs;
+            if (MODE == 1) {
+              dpe[3 + 6 * i + c] = f * cs;
+              dpe[6 + 6 * i + c] = -f * sn;
+            }
+            f *= 2.0f;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        // phase B: scale, split to fp16 hi/lo, scatter into the PE operand tile (64 columns x K=64)
+        for (int cidx = t; cidx < kTileN * 64; cidx += kEpiThreads) {
+          const int col = cidx >> 6, k = cidx & 63;
+          float v = 0.0f;
+          if (k < a.pe_dim) {
+            if (MODE == 0) {
+              v = scratch[col * kScratchStride + k];
+            } else {
+              const int pt = col >> 2, j = col & 3;
+              const int coord = k < 3 ? k : (k - 3) % 3;
+              v = j == 0 ? scratch[pt * kScratchStride + k]
+                         : (coord == j - 1 ? scratch[(kPtsPerTile + pt) * kScratchStride + k] : 0.0f);
+            }
+          }
+          const uint32_t o = xoff(col, k);
+          store_split(s_pehi + o, s_pelo + o, v * kActScale);
+        }
+      } else {
+        // render input [points(3), PE4(view)(27), normals(3), features(F)]  (implicit_differentiable_renderer.py:150)
+        if (t < kTileN) {
+          const long long gp = p0 + t;
+          float* pe = scratch + t * kScratchStride;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float vc = gp < n_pts ? __ldg(a.view + gp * 3 + c) : 0.0f;
+            pe[c] = vc;
+            float f = 1.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float sn, cs;
+              sincosf(vc * f, &sn, &cs);
+              pe[3 + 6 * i + c] = sn;
+              pe[6 + 6 * i + c] = cs;
+              f *= 2.0f;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        const int kpad = a.L[0].k_chunks * kChunkK;
+        const int F = a.feat_size;
+        for (int cidx = t; cidx < kTileN * kpad; cidx += kEpiThreads) {
+          const int col = cidx / kpad, k = cidx - col * kpad;
+          const long long gp = p0 + col;
+          float v = 0.0f;
+          if (gp < n_pts) {
+            if (k < 3) v = __ldg(a.x + gp * 3 + k);
+            else if (k < 30) v = scratch[col * kScratchStride + (k - 3)];
+            else if (k < 33) v = __ldg(a.normals + gp * 3 + (k - 30));
+            else if (k < 33 + F) v = __ldg(a.feats + gp * F + (k - 33));
+          }
+          const uint32_t o = xoff(col, k);
+          store_split(s_xhi + o, s_xlo + o, v * kActScale);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_act);
+
+      // ---------------- layers
+      for (int l = 0; l < a.n_run; ++l) {
+        const LayerPlan& lp = a.L[l];
+        const bool last = (l == a.n_run - 1);
+        ptx::mbar_wait(bar_acc, acc_ctr & 1);
+        ++acc_ctr;
+        ptx::tc_fence_after();
+        for (int m = 0; m < lp.m_tiles; ++m) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * kTileN + h * 32), v);
+          ptx::tmem_ld_wait();
+          const int f = m * kTileM + row;
+          const float bias = __ldg(a.bias + lp.bias_off + f);
+          if (!last) {
+            const uint32_t o0 = xoff(h * 32, f);
+            if (l == a.skip_layer - 1 && f >= a.skip_rows_begin) {
+              // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
+              const int k = f - a.skip_rows_begin;
+              const uint32_t s0 = xoff(h * 32, k);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                const bool real = k < a.pe_dim;
+                ptx::st_shared_u16(s_xhi + o0 + d, real ? ptx::ld_shared_u16(s_pehi + s0 + d) : (uint16_t)0);
+                ptx::st_shared_u16(s_xlo + o0 + d, real ? ptx::ld_shared_u16(s_pelo + s0 + d) : (uint16_t)0);
+              }
+            } else if (MODE == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float z = fmaf(__uint_as_float(v[j]), kInvScale, bias);
+                float y, sg;
+                if (lp.act == ACT_SOFTPLUS100) y = softplus100(z, sg);
+                else if (lp.act == ACT_RELU) y = fmaxf(z, 0.0f);
+                else y = z;
+                const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                store_split(s_xhi + o0 + d, s_xlo + o0 + d, y * kActScale);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float z = fmaf(__uint_as_float(v[4 * g]), kInvScale, bias);
+                float sg;
+                const float y = softplus100(z, sg);
+                const uint32_t d0 = (uint32_t)(((4 * g) >> 3) * 128 + ((4 * g) & 7) * 16);
+                store_split(s_xhi + o0 + d0, s_xlo + o0 + d0, y * kActScale);
+                const float ts = sg * (kInvScale * kActScale);
+#pragma unroll
+                for (int jj = 1; jj < 4; ++jj) {
+                  const uint32_t d = d0 + jj * 16;
+                  store_split(s_xhi + o0 + d, s_xlo + o0 + d, __uint_as_float(v[4 * g + jj]) * ts);
+                }
+              }
+            }
+          } else {
+            // ---------------- head: write results to global memory
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = h * 32 + j;
+              const float acc = __uint_as_float(v[j]) * kInvScale;
+              if (KIND == NET_RENDER) {
+                const long long gp = p0 + col;
+                if (row < 3 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
+              } else {
+                const long long gp = (MODE == 0) ? p0 + col : p0 + (col >> 2);
+                const int jj = (MODE == 0) ? 0 : (col & 3);
+                if (gp < n_pts) {
+                  if (a.head == HEAD_SDF_ONLY) {
+                    if (row == 0) {
+                      if (jj == 0) a.out_sdf[gp] = acc + bias;
+                      else a.out_grad[gp * 3 + jj - 1] = acc;
+                    }
+                  } else {
+                    const int F = a.feat_size;
+                    if (jj == 0) {
+                      if (f < F) a.out_full[gp * (F + 2) + 2 + f] = acc + bias;
+                      else if (f < F + 2) {
+                        a.out_full[gp * (F + 2) + (f - F)] = acc + bias;
+                        if (f == F && a.out_sdf) a.out_sdf[gp] = acc + bias;
+                      }
+                    } else if (f == F) {
+                      a.out_grad[gp * 3 + jj - 1] = acc;
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (!last) {
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_act);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace mvsdf

@@ -1,0 +1,75 @@
+"""GPU parity of the fused tcgen05 MLP tile kernels against the CPU oracle and the golden
+outputs of the reference (rows a3/a4/a5/a14 of SURVEY.md section 8).  All calls go through the C ABI."""
+import pytest
+import torch
+
+from oracle import mvsdf_oracle as O
+from tests.helpers import preset_state_dict, t
+
+pytestmark = pytest.mark.gpu
+
+TOL_SDF = 2e-5      # absolute, on O(1) SDF values: well inside the 1e-4 relative gate on depths
+TOL_GRAD = 1e-4
+TOL_RGB = 1e-4
+
+
+def _nets(preset, device):
+    from mvsdf_b200 import ops
+    from tests.helpers import WEIGHT_PRESETS
+    sd = preset_state_dict(preset)
+    w = WEIGHT_PRESETS[preset]["width"]
+    sdf = ops.PackedNet("sdf", w, 8).pack_state_dict(sd, "implicit_network", device)
+    rend = ops.PackedNet("render", w, 4, n_freqs=4).pack_state_dict(sd, "rendering_network", device)
+    return sd, sdf, rend
+
+
+@pytest.mark.parametrize("name", ["mlp_w256", "mlp_w512"])
+def test_mlp_vs_reference_golden(golden, name):
+    from mvsdf_b200 import ops
+    g = golden(name)
+    dev = torch.device("cuda:0")
+    sd, sdf, rend = _nets(str(g["meta_preset"]), dev)
+    x = t(g["x"]).to(dev)
+    full = ops.sdf_forward(sdf, x, ops.HEAD_FULL).cpu()
+    ref = t(g["sdf_full"])
+    assert (full - ref).abs().max().item() < TOL_SDF, (full - ref).abs().max().item()
+    s = ops.sdf_forward(sdf, x, ops.HEAD_SDF_ONLY).cpu()
+    assert (s - ref[:, 0]).abs().max().item() < TOL_SDF
+    full2, grad = ops.sdf_value_grad(sdf, x, ops.HEAD_FULL)
+    assert (full2.cpu() - ref).abs().max().item() < TOL_SDF
+    assert (grad.cpu() - t(g["grad"])).abs().max().item() < TOL_GRAD
+    s3, grad3 = ops.sdf_value_grad(sdf, x, ops.HEAD_SDF_ONLY)
+    assert (s3.cpu() - ref[:, 0]).abs().max().item() < TOL_SDF
+    assert (grad3.cpu() - t(g["grad"])).abs().max().item() < TOL_GRAD
+    rgb = ops.render_forward(rend, x, t(g["view"]).to(dev), t(g["grad"]).to(dev), ref[:, 2:].contiguous().to(dev))
+    assert (rgb.cpu() - t(g["rgb"])).abs().max().item() < TOL_RGB
+
+
+@pytest.mark.parametrize("preset,n", [("w256", 1), ("w256", 63), ("w256", 65), ("w512", 5000), ("w512", 100003)])
+def test_mlp_vs_oracle_ragged_sizes(preset, n):
+    """Empty / ragged / multi-wave point counts against the oracle (fp32) with an fp64 tie-breaker."""
+    from mvsdf_b200 import ops
+    dev = torch.device("cuda:0")
+    sd, sdf, rend = _nets(preset, dev)
+    gen = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=gen) * 2 - 1)
+    m = min(n, 4096)                      # the CPU oracle checks a bounded sample
+    idx = torch.randperm(n, generator=gen)[:m]
+    w64 = O.sdf_weights(sd, dtype=torch.float64)
+    with torch.no_grad():
+        ref64 = O.sdf_mlp(x[idx].double(), w64)
+    gref = O.sdf_gradient(x[idx].double(), w64)
+    full, grad = ops.sdf_value_grad(sdf, x.to(dev), ops.HEAD_FULL)
+    assert (full.cpu()[idx].double() - ref64).abs().max().item() < TOL_SDF
+    assert (grad.cpu()[idx].double() - gref).abs().max().item() < TOL_GRAD
+    s = ops.sdf_forward(sdf, x.to(dev), ops.HEAD_SDF_ONLY)
+    assert (s.cpu()[idx].double() - ref64[:, 0]).abs().max().item() < TOL_SDF
+    torch.cuda.synchronize()
+
+
+def test_mlp_empty_batch():
+    from mvsdf_b200 import ops
+    dev = torch.device("cuda:0")
+    sd, sdf, rend = _nets("w256", dev)
+    out = ops.sdf_forward(sdf, torch.zeros(0, 3, device=dev), ops.HEAD_SDF_ONLY)
+    assert out.shape == (0,)
