@@ -71,6 +71,73 @@ int mvsdf_render_forward(const mvsdf_net* net, const void* packed, const float* 
                          const float* normals, const float* features, int64_t n, const int32_t* n_dev, float* out_rgb,
                          void* stream);
 
+/* ---- RayTracing (code/model/ray_tracing.py) ---------------------------------------------------------
+ * Constructor arguments of RayTracing.__init__ (:6-25; values in confs/mvsdf_dtu.conf:49-58) plus the two
+ * hard-coded switches of sphere_tracing (:127-131): dist_clip = 0.5 (0.05 and 40 iterations under IDR_RENDER). */
+typedef struct mvsdf_tracer_params {
+  float object_bounding_sphere;
+  float sdf_threshold;
+  float line_search_step;
+  float dist_clip;
+  int line_step_iters;
+  int sphere_tracing_iters;
+  int n_steps;            /* must be 100 */
+  int n_secant_steps;
+  int skip_min_sdf;       /* training only: drop minimal_sdf_points (:280-308), whose outputs no MVSDF loss reads */
+} mvsdf_tracer_params;
+
+#define MVSDF_NUM_TRACE_COUNTERS 128
+
+size_t mvsdf_trace_workspace_bytes(int64_t n_rays, int n_images);
+
+/* get_camera_params + lift (code/utils/rend_util.py:48-100), get_sphere_intersection (:141-162) and
+ * RayTracing.forward (ray_tracing.py:27-98: sphere_tracing :101-196, ray_sampler :198-258, secant :260-278,
+ * minimal_sdf_points :280-308) for n_images x n_pixels rays, with the SDF supplied as packed weights instead of
+ * the Python closure of implicit_differentiable_renderer.py:194.
+ *   uv [B,N,2] (x=col,y=row), pose [B,4,4] cam->world, intrinsics [B,4,4], object_mask [B*N] uint8 or NULL (= all ones);
+ *   linspace100 [100] = torch.linspace(0,1,100) (ray_tracing.py:206); steps01 [100] ~ U(0,1) drawn by the caller from
+ *   the CPU generator exactly like ray_tracing.py:287 (training only).
+ * Outputs: out_ray_dirs [B*N,3], out_cam_loc [B,3] (optional), out_dists [B*N], out_net_mask [B*N] uint8
+ *   (network_object_mask), out_points [B*N,3] (optional; cam_loc + dists*ray_dirs, :200 of the renderer),
+ *   out_counters [MVSDF_NUM_TRACE_COUNTERS] int32 (optional; SDF evaluations requested per phase, their sum is E_trace). */
+int mvsdf_trace(const mvsdf_net* sdf_net, const void* sdf_packed, const float* uv, const float* pose,
+                const float* intrinsics, const uint8_t* object_mask, const mvsdf_tracer_params* params, int n_images,
+                int n_pixels, int training, const float* linspace100, const float* steps01, size_t workspace_bytes,
+                void* workspace, float* out_ray_dirs, float* out_cam_loc, float* out_dists, uint8_t* out_net_mask,
+                float* out_points, int32_t* out_counters, void* stream);
+
+/* ---- IDRNetwork.forward after the tracer (implicit_differentiable_renderer.py:200-213, :295-304) and
+ * get_rbg_value (:324-338): sdf_output for every ray, order-preserving gather of the surface rays, fused
+ * value + analytic normal + feature pass, surface light field, scatter into rgb_values (ones where missed).
+ *   surface_mask [R] uint8 (network_object_mask, AND object_mask in training);
+ *   out_sdf [R] (optional), out_rgb_values [R,3], out_surf_pts / out_normals [R,3] (first M rows valid),
+ *   out_surf_head [R,2] (optional: sdf and surface-indicator logit of the M surface points),
+ *   out_hit_index [R] (ray index of each surface point), out_hit_offsets [B+1] (per-image exclusive offsets, [B] = M). */
+size_t mvsdf_shade_workspace_bytes(int64_t n_rays, int feature_size);
+int mvsdf_shade_rays(const mvsdf_net* sdf_net, const void* sdf_packed, const mvsdf_net* render_net,
+                     const void* render_packed, const float* ray_dirs, const float* points, const uint8_t* surface_mask,
+                     int n_images, int n_pixels, int feature_size, size_t workspace_bytes, void* workspace,
+                     float* out_sdf, float* out_rgb_values, float* out_surf_pts, float* out_normals, float* out_surf_head,
+                     int32_t* out_hit_index, int32_t* out_hit_offsets, void* stream);
+
+/* ---- IDRLoss.get_feat_loss_corr (code/model/loss.py:115-165; helpers code/utils/my_utils.py:98-165) ---------
+ * Feature maps are constants of the scene (scene_dataset.py:141-149): restack them once into channels-last with
+ * mvsdf_feat_nchw_to_nhwc ([n,32,h,w] -> [n,h,w,32]) so that every bilinear tap is one 128-byte load.
+ *   surf_pts [M,3] packed by image (diff_surf_pts), hit_offsets [B+1] device int32, cams [B,V,2,4,4] (reference view
+ *   first, then the sources; cam[.,0] = 4x4 extrinsic, cam[.,1,:3,:3] = K), maps_nhwc [B,V,h,w,32], size [1], center [3].
+ * partials [B,2] float64 = (sum of kept |1-corr|, (V-1)*m_i): this is what a multi-GPU run all-reduces;
+ * finalize forms mean_i(sum_i / count_i) exactly like loss.py:155-163. */
+int mvsdf_feat_nchw_to_nhwc(const float* src, int n, int channels, int h, int w, float* dst, void* stream);
+int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, const float* cams, const float* maps_nhwc,
+                             int n_images, int n_views, int h, int w, int channels, const float* size,
+                             const float* center, double* partials, void* stream);
+int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_loss, void* stream);
+
+/* ---- IDRLoss.get_rgb_loss (loss.py:21-28): sum |rgb - gt| over mask / n_rays.  partials [2] float64 = (sum, n_rays). */
+int mvsdf_rgb_l1_partials(const float* rgb_values, const float* rgb_gt, const uint8_t* mask, int64_t n_rays,
+                          double* partials, void* stream);
+int mvsdf_rgb_l1_finalize(const double* partials, float* out_loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,24 +41,30 @@ def _declare(lib):
     lib.mvsdf_sdf_value_grad.argtypes = [P, P, P, c_int64, P, c_int, P, P, P, P]
     lib.mvsdf_render_forward.restype = c_int
     lib.mvsdf_render_forward.argtypes = [P, P, P, P, P, P, c_int64, P, P, P]
-    # part 2 (tracer / shading / losses) is declared when present
-    if hasattr(lib, "mvsdf_trace_workspace_bytes"):
-        lib.mvsdf_trace_workspace_bytes.restype = c_size_t
-        lib.mvsdf_trace_workspace_bytes.argtypes = [c_int64, c_int]
-        lib.mvsdf_trace.restype = c_int
-        lib.mvsdf_trace.argtypes = [P, P, P, P, P, P, P, c_int, c_int, c_int, P, P, c_size_t, P, P, P, P, P, P, P]
-    if hasattr(lib, "mvsdf_render_rays_workspace_bytes"):
-        lib.mvsdf_render_rays_workspace_bytes.restype = c_size_t
-        lib.mvsdf_render_rays_workspace_bytes.argtypes = [c_int64]
-        lib.mvsdf_render_rays.restype = c_int
-        lib.mvsdf_render_rays.argtypes = [P, P, P, P, P, P, P, P, c_int64, P, c_size_t, P, P, P, P, P, P, P]
-    if hasattr(lib, "mvsdf_feat_nchw_to_nhwc"):
-        lib.mvsdf_feat_nchw_to_nhwc.restype = c_int
-        lib.mvsdf_feat_nchw_to_nhwc.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
-        lib.mvsdf_feat_loss_corr.restype = c_int
-        lib.mvsdf_feat_loss_corr.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
-        lib.mvsdf_rgb_l1.restype = c_int
-        lib.mvsdf_rgb_l1.argtypes = [P, P, P, P, c_int64, P, P]
+    class TracerParams(ctypes.Structure):
+        _fields_ = [("object_bounding_sphere", c_float), ("sdf_threshold", c_float), ("line_search_step", c_float),
+                    ("dist_clip", c_float), ("line_step_iters", c_int), ("sphere_tracing_iters", c_int),
+                    ("n_steps", c_int), ("n_secant_steps", c_int), ("skip_min_sdf", c_int)]
+    lib.TracerParams = TracerParams
+    lib.mvsdf_trace_workspace_bytes.restype = c_size_t
+    lib.mvsdf_trace_workspace_bytes.argtypes = [c_int64, c_int]
+    lib.mvsdf_trace.restype = c_int
+    lib.mvsdf_trace.argtypes = [P, P, P, P, P, P, POINTER(TracerParams), c_int, c_int, c_int, P, P, c_size_t, P,
+                                P, P, P, P, P, P, P]
+    lib.mvsdf_shade_workspace_bytes.restype = c_size_t
+    lib.mvsdf_shade_workspace_bytes.argtypes = [c_int64, c_int]
+    lib.mvsdf_shade_rays.restype = c_int
+    lib.mvsdf_shade_rays.argtypes = [P, P, P, P, P, P, P, c_int, c_int, c_int, c_size_t, P, P, P, P, P, P, P, P, P]
+    lib.mvsdf_feat_nchw_to_nhwc.restype = c_int
+    lib.mvsdf_feat_nchw_to_nhwc.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
+    lib.mvsdf_feat_loss_partials.restype = c_int
+    lib.mvsdf_feat_loss_partials.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
+    lib.mvsdf_feat_loss_finalize.restype = c_int
+    lib.mvsdf_feat_loss_finalize.argtypes = [P, c_int, P, P]
+    lib.mvsdf_rgb_l1_partials.restype = c_int
+    lib.mvsdf_rgb_l1_partials.argtypes = [P, P, P, c_int64, P, P]
+    lib.mvsdf_rgb_l1_finalize.restype = c_int
+    lib.mvsdf_rgb_l1_finalize.argtypes = [P, P, P]
     return lib
 
 

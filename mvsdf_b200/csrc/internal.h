@@ -17,6 +17,6 @@ int sm_count();
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,
             float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st);
 int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const float* view, const float* normals,
-               const float* feats, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st);
+               const float* feats, int feat_stride, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st);
 
 }  // namespace mvsdf

@@ -174,7 +174,7 @@ int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n,
 }
 
 int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const float* view, const float* normals,
-               const float* feats, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st) {
+               const float* feats, int feat_stride, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st) {
   if (!net || net->plan.kind != NET_RENDER) return fail(MVSDF_ERR_INVALID, "expected a rendering net plan");
   if (!packed || n < 0 || !rgb || ((!pts || !view || !normals || !feats) && n > 0))
     return fail(MVSDF_ERR_INVALID, "null pointer / negative count");
@@ -184,6 +184,7 @@ int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const
   a.view = view;
   a.normals = normals;
   a.feats = feats;
+  a.feat_stride = feat_stride > 0 ? feat_stride : net->plan.feat_size;
   a.out_rgb = rgb;
   return launch_mlp<NET_RENDER, 0>(net->plan, a, n, n_dev, st);
 }
@@ -332,7 +333,7 @@ int mvsdf_sdf_value_grad(const mvsdf_net* net, const void* packed, const float* 
 int mvsdf_render_forward(const mvsdf_net* net, const void* packed, const float* points, const float* view_dirs,
                          const float* normals, const float* features, int64_t n, const int32_t* n_dev, float* out_rgb,
                          void* stream) {
-  return mlp_render(net, packed, points, view_dirs, normals, features, n, n_dev, out_rgb,
+  return mlp_render(net, packed, points, view_dirs, normals, features, 0, n, n_dev, out_rgb,
                     static_cast<cudaStream_t>(stream));
 }
 

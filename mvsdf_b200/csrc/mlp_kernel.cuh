@@ -45,6 +45,7 @@ struct MlpArgs {
   int k_cores_max;
   int head;                  // HeadKind
   int feat_size;
+  int feat_stride;           // row stride (floats) of `feats`; lets the render pass read full[:, 2:] in place
   long long n;               // number of points (ignored when n_ptr != nullptr)
   const int* n_ptr;          // optional device-side count
   const float* x;            // [n,3]
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
             if (k < 3) v = __ldg(a.x + gp * 3 + k);
             else if (k < 30) v = scratch[col * kScratchStride + (k - 3)];
             else if (k < 33) v = __ldg(a.normals + gp * 3 + (k - 30));
-            else if (k < 33 + F) v = __ldg(a.feats + gp * F + (k - 33));
+            else if (k < 33 + F) v = __ldg(a.feats + gp * a.feat_stride + (k - 33));
           }
           const uint32_t o = xoff(col, k);
           store_split(s_xhi + o, s_xlo + o, v * kActScale);

@@ -1,0 +1,555 @@
+// C ABI, part 2: the ray tracer (rows a1, a2, a6-a10 of SURVEY.md section 8).
+//
+// RayTracing.forward (code/model/ray_tracing.py:27-98) re-expressed as a request server around the
+// fused SDF-MLP tile kernel: small per-ray state-machine kernels emit "evaluate the SDF at
+// (ray, t)" requests into a compacted device-side list, the persistent tcgen05 kernel evaluates
+// whatever count the device counter holds, and the next state kernel consumes the results.
+// There is no host synchronisation, no boolean-mask indexing and no .sum() test anywhere: the
+// reference's global early-exit tests (ray_tracing.py:153,176) are pure optimisations, the per-ray
+// semantics below are identical.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+
+#include "../../include/mvsdf_b200.h"
+#include "internal.h"
+
+namespace mvsdf {
+
+constexpr int kBlock = 256;
+constexpr int kSteps = 100;          // n_steps must be 100 (confs/mvsdf_dtu.conf:56); checked at the ABI
+
+enum RayFlag : uint32_t {
+  F_HIT_SPHERE = 1u << 0,
+  F_LIVE_S = 1u << 1,
+  F_LIVE_E = 1u << 2,
+  F_OVER_S = 1u << 3,
+  F_OVER_E = 1u << 4,
+  F_SAMPLER = 1u << 5,
+  F_NET = 1u << 6,       // network_object_mask
+  F_SECANT = 1u << 7,
+  F_MINSDF = 1u << 8,
+};
+
+struct RayState {
+  // all arrays have one entry per ray
+  float* dir;        // [R,3]
+  float* acc_s;
+  float* acc_e;
+  float* min_dis;
+  float* max_dis;
+  float* next_s;
+  float* next_e;
+  float* cur_s;
+  float* cur_e;
+  int* slot_s;       // pending request slots (or -1)
+  int* slot_e;
+  uint32_t* flags;
+  // secant state
+  float* z_lo;
+  float* z_hi;
+  float* f_lo;
+  float* f_hi;
+  float* z;
+  int* list;         // compacted ray list (sampler / min-sdf)
+  int* list_pos;     // position of a ray inside the list (sampler batches)
+};
+
+struct TraceCtx {
+  RayState s;
+  const float* cam;  // [B,3]
+  float* req_pts;    // [cap,3]
+  float* req_val;    // [cap]
+  int* counters;     // [kNumCounters]
+  int R, N;
+  long long cap;
+  float thr, clip, line_step;
+};
+
+__device__ __forceinline__ float3 ray_point(const float* cam, const float* dir, float t) {
+  // cam + t * dir with separate multiply and add, like the reference's elementwise torch ops
+  return make_float3(__fadd_rn(cam[0], __fmul_rn(t, dir[0])), __fadd_rn(cam[1], __fmul_rn(t, dir[1])),
+                     __fadd_rn(cam[2], __fmul_rn(t, dir[2])));
+}
+
+__device__ __forceinline__ int push_request(const TraceCtx& c, int counter, float3 p) {
+  const int slot = atomicAdd(c.counters + counter, 1);
+  c.req_pts[3 * (size_t)slot + 0] = p.x;
+  c.req_pts[3 * (size_t)slot + 1] = p.y;
+  c.req_pts[3 * (size_t)slot + 2] = p.z;
+  return slot;
+}
+
+__device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf(v, -lim), lim); }
+
+// ---- a1 + a2 + tracer initialisation (rend_util.py:48-100, :141-162; ray_tracing.py:104-137)
+__global__ void ray_setup_kernel(TraceCtx c, const float* __restrict__ uv, const float* __restrict__ pose,
+                                 const float* __restrict__ intr, float* __restrict__ cam_out, float radius, int counter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  const int b = r / c.N;
+  const float* P = pose + 16 * b;
+  const float* K = intr + 16 * b;
+  const float fx = K[0], sk = K[1], cx = K[2], fy = K[5], cy = K[6];
+  const float x = uv[2 * (size_t)r] + 0.5f, y = uv[2 * (size_t)r + 1] + 0.5f;
+  // lift() with z = 1:  (x - cx + cy*sk/fy - sk*y/fy) / fx ,  (y - cy) / fy
+  const float xl = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(x, cx), __fdiv_rn(__fmul_rn(cy, sk), fy)),
+                                       __fdiv_rn(__fmul_rn(sk, y), fy)), fx);
+  const float yl = __fdiv_rn(__fsub_rn(y, cy), fy);
+  float d[3], cam[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    cam[i] = P[4 * i + 3];
+    const float w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[4 * i], xl), __fmul_rn(P[4 * i + 1], yl)), P[4 * i + 2]),
+                              P[4 * i + 3]);
+    d[i] = __fsub_rn(w, cam[i]);
+  }
+  const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]))), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d[i] = __fdiv_rn(d[i], nrm);
+    c.s.dir[3 * (size_t)r + i] = d[i];
+  }
+  if (r % c.N == 0) {
+    cam_out[3 * b] = cam[0];
+    cam_out[3 * b + 1] = cam[1];
+    cam_out[3 * b + 2] = cam[2];
+  }
+  const float dc = __fadd_rn(__fadd_rn(__fmul_rn(d[0], cam[0]), __fmul_rn(d[1], cam[1])), __fmul_rn(d[2], cam[2]));
+  const float cn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cam[0], cam[0]), __fmul_rn(cam[1], cam[1])), __fmul_rn(cam[2], cam[2])));
+  const float under = __fsub_rn(__fmul_rn(dc, dc), __fsub_rn(__fmul_rn(cn, cn), radius * radius));
+  uint32_t fl = 0;
+  float t0 = 0.f, t1 = 0.f;
+  if (under > 0.f) {
+    const float rt = sqrtf(under);
+    t0 = fmaxf(__fsub_rn(-rt, dc), 0.f);
+    t1 = fmaxf(__fsub_rn(rt, dc), 0.f);
+    fl = F_HIT_SPHERE | F_LIVE_S | F_LIVE_E;
+  }
+  c.s.acc_s[r] = t0;
+  c.s.acc_e[r] = t1;
+  c.s.min_dis[r] = t0;
+  c.s.max_dis[r] = t1;
+  c.s.next_s[r] = 0.f;
+  c.s.next_e[r] = 0.f;
+  c.s.cur_s[r] = 0.f;
+  c.s.cur_e[r] = 0.f;
+  int ss = -1, se = -1;
+  if (fl) {
+    ss = push_request(c, counter, ray_point(cam, d, t0));
+    se = push_request(c, counter, ray_point(cam, d, t1));
+  }
+  c.s.slot_s[r] = ss;
+  c.s.slot_e[r] = se;
+  c.s.flags[r] = fl;
+}
+
+__device__ __forceinline__ void collect(const TraceCtx& c, int r) {
+  const int ss = c.s.slot_s[r], se = c.s.slot_e[r];
+  if (ss >= 0) {
+    c.s.next_s[r] = clampf(c.req_val[ss], c.clip);
+    c.s.slot_s[r] = -1;
+  }
+  if (se >= 0) {
+    c.s.next_e[r] = clampf(c.req_val[se], c.clip);
+    c.s.slot_e[r] = -1;
+  }
+}
+
+// top of the while-loop body (ray_tracing.py:139-171); `first`: no end-of-body update yet; `last`: iters == max
+__global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  uint32_t fl = c.s.flags[r];
+  if (!(fl & F_HIT_SPHERE)) return;
+  collect(c, r);
+  float acc_s = c.s.acc_s[r], acc_e = c.s.acc_e[r];
+  if (!first) {   // end of the previous body (:193-194)
+    if (!(acc_s < acc_e)) fl &= ~(F_LIVE_S | F_LIVE_E);
+  }
+  float cur_s = (fl & F_LIVE_S) ? c.s.next_s[r] : 0.f;
+  if (cur_s <= c.thr) cur_s = 0.f;
+  float cur_e = (fl & F_LIVE_E) ? c.s.next_e[r] : 0.f;
+  if (cur_e <= c.thr) cur_e = 0.f;
+  if (!(cur_s > c.thr)) fl &= ~F_LIVE_S;
+  if (!(cur_e > c.thr)) fl &= ~F_LIVE_E;
+  fl &= ~(F_OVER_S | F_OVER_E);
+  c.s.cur_s[r] = cur_s;
+  c.s.cur_e[r] = cur_e;
+  if (!last) {
+    acc_s = __fadd_rn(acc_s, cur_s);
+    acc_e = __fsub_rn(acc_e, cur_e);
+    c.s.acc_s[r] = acc_s;
+    c.s.acc_e[r] = acc_e;
+    const float* cam = c.cam + 3 * (r / c.N);
+    const float* d = c.s.dir + 3 * (size_t)r;
+    c.s.next_s[r] = 0.f;
+    c.s.next_e[r] = 0.f;
+    if (fl & F_LIVE_S) c.s.slot_s[r] = push_request(c, counter, ray_point(cam, d, acc_s));
+    if (fl & F_LIVE_E) c.s.slot_e[r] = push_request(c, counter, ray_point(cam, d, acc_e));
+  }
+  c.s.flags[r] = fl;
+}
+
+// one pass of the overshoot back-off loop (ray_tracing.py:173-191)
+__global__ void trace_backoff_kernel(TraceCtx c, int k, int counter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  const uint32_t fl = c.s.flags[r];
+  if (!(fl & F_HIT_SPHERE)) return;
+  collect(c, r);
+  const float back = (1.0f - c.line_step) / (float)(1 << k);
+  const float* cam = c.cam + 3 * (r / c.N);
+  const float* d = c.s.dir + 3 * (size_t)r;
+  if (c.s.next_s[r] < 0.f) {
+    const float a = __fsub_rn(c.s.acc_s[r], __fmul_rn(back, c.s.cur_s[r]));
+    c.s.acc_s[r] = a;
+    c.s.slot_s[r] = push_request(c, counter, ray_point(cam, d, a));
+  }
+  if (c.s.next_e[r] < 0.f) {
+    const float a = __fadd_rn(c.s.acc_e[r], __fmul_rn(back, c.s.cur_e[r]));
+    c.s.acc_e[r] = a;
+    c.s.slot_e[r] = push_request(c, counter, ray_point(cam, d, a));
+  }
+}
+
+// after the loop: network_object_mask = acc_s < acc_e (:41); unconverged start rays go to the sampler (:44)
+__global__ void trace_finish_kernel(TraceCtx c, int list_counter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  uint32_t fl = c.s.flags[r];
+  fl &= ~(F_NET | F_SAMPLER | F_SECANT | F_MINSDF);
+  if (c.s.acc_s[r] < c.s.acc_e[r]) fl |= F_NET;
+  c.s.list_pos[r] = -1;
+  if (fl & F_LIVE_S) {
+    fl |= F_SAMPLER;
+    const int pos = atomicAdd(c.counters + list_counter, 1);
+    c.s.list[pos] = r;
+    c.s.list_pos[r] = pos;
+  }
+  c.s.flags[r] = fl;
+}
+
+// sampler batch: 100 samples on [acc_s, acc_e] for list entries [begin, begin+batch)  (:206-219)
+__global__ void sampler_push_kernel(TraceCtx c, const float* __restrict__ lin, int list_counter, int begin, int batch,
+                                    int counter) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.counters[counter] = total * kSteps;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over batch * 100
+  if (idx >= total * kSteps) return;
+  const int li = idx / kSteps, i = idx - li * kSteps;
+  const int r = c.s.list[begin + li];
+  const float lo = c.s.acc_s[r], hi = c.s.acc_e[r];
+  const float t = __fadd_rn(lo, __fmul_rn(lin[i], __fsub_rn(hi, lo)));
+  const float3 p = ray_point(c.cam + 3 * (r / c.N), c.s.dir + 3 * (size_t)r, t);
+  c.req_pts[3 * (size_t)idx] = p.x;
+  c.req_pts[3 * (size_t)idx + 1] = p.y;
+  c.req_pts[3 * (size_t)idx + 2] = p.z;
+}
+
+// first sign change / arg-min selection and secant initialisation (:221-256); one thread per sampler ray
+__global__ void sampler_select_kernel(TraceCtx c, const float* __restrict__ lin, const uint8_t* __restrict__ obj_mask,
+                                      int training, int list_counter, int begin, int batch) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= total) return;
+  const int r = c.s.list[begin + li];
+  const float* f = c.req_val + (size_t)li * kSteps;
+  const float lo = c.s.acc_s[r], hi = c.s.acc_e[r];
+  int first_neg = -1, first_zero = -1, amin = 0;
+  float fmin_ = f[0];
+  for (int i = 0; i < kSteps; ++i) {
+    const float v = f[i];
+    if (v < 0.f && first_neg < 0) first_neg = i;
+    if (v == 0.f && first_zero < 0) first_zero = i;
+    if (v < fmin_) {
+      fmin_ = v;
+      amin = i;
+    }
+  }
+  const int first = first_neg >= 0 ? first_neg : (first_zero >= 0 ? first_zero : kSteps - 1);
+  const bool inside_net = f[first] < 0.f;
+  const bool inside_true = obj_mask ? obj_mask[r] != 0 : true;
+  uint32_t fl = c.s.flags[r];
+  fl &= ~F_NET;
+  if (inside_net) fl |= F_NET;
+  const float span = __fsub_rn(hi, lo);
+  int pick = first;
+  if (!(inside_true && inside_net)) pick = amin;                     // P_out: sample of minimal SDF (:230-235)
+  float t_out = __fadd_rn(lo, __fmul_rn(lin[pick], span));
+  const bool sec = training ? (inside_net && inside_true) : inside_net;
+  if (sec) {
+    const int prev = first == 0 ? kSteps - 1 : first - 1;            // python's [-1] wrap (:248-249)
+    const float z_hi = __fadd_rn(lo, __fmul_rn(lin[first], span));
+    const float z_lo = __fadd_rn(lo, __fmul_rn(lin[prev], span));
+    const float f_hi = f[first], f_lo = f[prev];
+    const float z = __fadd_rn(__fdiv_rn(__fmul_rn(-f_lo, __fsub_rn(z_hi, z_lo)), __fsub_rn(f_hi, f_lo)), z_lo);
+    c.s.z_lo[r] = z_lo;
+    c.s.z_hi[r] = z_hi;
+    c.s.f_lo[r] = f_lo;
+    c.s.f_hi[r] = f_hi;
+    c.s.z[r] = z;
+    fl |= F_SECANT;
+    t_out = z;
+  }
+  c.s.acc_s[r] = t_out;
+  c.s.flags[r] = fl;
+}
+
+// secant iterations (:260-278): `collect_prev` consumes f(z) of the previous request, `push` issues the next
+__global__ void secant_kernel(TraceCtx c, int list_counter, int collect_prev, int push, int counter) {
+  const int total = c.counters[list_counter];
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= total) return;
+  const int r = c.s.list[li];
+  if (!(c.s.flags[r] & F_SECANT)) return;
+  float z = c.s.z[r];
+  if (collect_prev) {
+    const float fm = c.req_val[c.s.slot_s[r]];
+    float z_lo = c.s.z_lo[r], z_hi = c.s.z_hi[r], f_lo = c.s.f_lo[r], f_hi = c.s.f_hi[r];
+    if (fm > 0.f) {
+      z_lo = z;
+      f_lo = fm;
+    }
+    if (fm < 0.f) {
+      z_hi = z;
+      f_hi = fm;
+    }
+    z = __fadd_rn(__fdiv_rn(__fmul_rn(-f_lo, __fsub_rn(z_hi, z_lo)), __fsub_rn(f_hi, f_lo)), z_lo);
+    c.s.z_lo[r] = z_lo;
+    c.s.z_hi[r] = z_hi;
+    c.s.f_lo[r] = f_lo;
+    c.s.f_hi[r] = f_hi;
+    c.s.z[r] = z;
+    c.s.acc_s[r] = z;
+  }
+  if (push) c.s.slot_s[r] = push_request(c, counter, ray_point(c.cam + 3 * (r / c.N), c.s.dir + 3 * (size_t)r, z));
+}
+
+// training only (:73-94): closest approach for rays that miss the sphere; list the rays for minimal_sdf_points
+__global__ void minsdf_prepare_kernel(TraceCtx c, const uint8_t* __restrict__ obj_mask, int list_counter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  uint32_t fl = c.s.flags[r];
+  const bool obj = obj_mask ? obj_mask[r] != 0 : true;
+  const bool net = fl & F_NET, samp = fl & F_SAMPLER, hs = fl & F_HIT_SPHERE;
+  const bool in_m = !net && obj && !samp;
+  const bool out_m = !obj && !samp;
+  if (!(in_m || out_m)) return;
+  if (!hs) {
+    const float* cam = c.cam + 3 * (r / c.N);
+    const float* d = c.s.dir + 3 * (size_t)r;
+    c.s.acc_s[r] = -__fadd_rn(__fadd_rn(__fmul_rn(d[0], cam[0]), __fmul_rn(d[1], cam[1])), __fmul_rn(d[2], cam[2]));
+    return;
+  }
+  if (net && out_m) c.s.min_dis[r] = c.s.acc_s[r];
+  fl |= F_MINSDF;
+  c.s.flags[r] = fl;
+  const int pos = atomicAdd(c.counters + list_counter, 1);
+  c.s.list[pos] = r;
+}
+
+__global__ void minsdf_push_kernel(TraceCtx c, const float* __restrict__ steps01, int list_counter, int begin, int batch,
+                                   int counter) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.counters[counter] = total * kSteps;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total * kSteps) return;
+  const int li = idx / kSteps, i = idx - li * kSteps;
+  const int r = c.s.list[begin + li];
+  const float lo = c.s.min_dis[r], hi = c.s.max_dis[r];
+  const float t = __fadd_rn(__fmul_rn(steps01[i], __fsub_rn(hi, lo)), lo);
+  const float3 p = ray_point(c.cam + 3 * (r / c.N), c.s.dir + 3 * (size_t)r, t);
+  c.req_pts[3 * (size_t)idx] = p.x;
+  c.req_pts[3 * (size_t)idx + 1] = p.y;
+  c.req_pts[3 * (size_t)idx + 2] = p.z;
+}
+
+__global__ void minsdf_select_kernel(TraceCtx c, const float* __restrict__ steps01, int list_counter, int begin, int batch) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= total) return;
+  const int r = c.s.list[begin + li];
+  const float* f = c.req_val + (size_t)li * kSteps;
+  int amin = 0;
+  float fm = f[0];
+  for (int i = 1; i < kSteps; ++i)
+    if (f[i] < fm) {
+      fm = f[i];
+      amin = i;
+    }
+  const float lo = c.s.min_dis[r], hi = c.s.max_dis[r];
+  c.s.acc_s[r] = __fadd_rn(__fmul_rn(steps01[amin], __fsub_rn(hi, lo)), lo);
+}
+
+__global__ void trace_output_kernel(TraceCtx c, float* __restrict__ dists, uint8_t* __restrict__ net_mask,
+                                    float* __restrict__ points) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  const float t = c.s.acc_s[r];
+  dists[r] = t;
+  net_mask[r] = (c.s.flags[r] & F_NET) ? 1 : 0;
+  if (points) {   // IDRNetwork.forward recomputes points = cam_loc + dists * ray_dirs (:200)
+    const float3 p = ray_point(c.cam + 3 * (r / c.N), c.s.dir + 3 * (size_t)r, t);
+    points[3 * (size_t)r] = p.x;
+    points[3 * (size_t)r + 1] = p.y;
+    points[3 * (size_t)r + 2] = p.z;
+  }
+}
+
+constexpr int kNumCounters = 128;
+
+struct WorkspaceLayout {
+  size_t off_counters, off_cam, off_f[9], off_i[4], off_flags, off_req_pts, off_req_val, total;
+  long long cap;
+  int batch_rays;
+};
+
+static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
+  WorkspaceLayout w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  w.off_counters = take(kNumCounters * 4);
+  w.off_cam = take((size_t)B * 3 * 4);
+  for (int i = 0; i < 9; ++i) w.off_f[i] = take((size_t)R * 4);       // acc_s acc_e min max next_s next_e cur_s cur_e z
+  for (int i = 0; i < 4; ++i) w.off_i[i] = take((size_t)R * 4);       // slot_s slot_e list list_pos
+  w.off_flags = take((size_t)R * 4);
+  w.batch_rays = (int)std::min<int64_t>(R, batch_rays);
+  w.cap = std::max<long long>(2 * R, (long long)w.batch_rays * kSteps);
+  w.off_req_pts = take((size_t)w.cap * 12);
+  w.off_req_val = take((size_t)w.cap * 4);
+  w.total = off;
+  return w;
+}
+
+}  // namespace mvsdf
+
+using namespace mvsdf;
+
+extern "C" {
+
+size_t mvsdf_trace_workspace_bytes(int64_t n_rays, int n_images) {
+  // 4 extra float arrays for the secant state live in the tail
+  return layout_for(n_rays, n_images, 1 << 18).total + (size_t)n_rays * 4 * 4 + 1024;
+}
+
+int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const float* pose, const float* intrinsics,
+                const uint8_t* object_mask, const mvsdf_tracer_params* prm, int n_images, int n_pixels, int training,
+                const float* linspace100, const float* steps01, size_t workspace_bytes, void* workspace,
+                float* out_ray_dirs, float* out_cam_loc, float* out_dists, uint8_t* out_net_mask, float* out_points,
+                int32_t* out_counters, void* stream) {
+  if (!net || !packed || !uv || !pose || !intrinsics || !prm || !workspace || !out_ray_dirs || !out_dists ||
+      !out_net_mask || !linspace100)
+    return fail(MVSDF_ERR_INVALID, "mvsdf_trace: null argument");
+  if (prm->n_steps != kSteps) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: n_steps must be %d", kSteps);
+  if (prm->line_step_iters < 0 || prm->line_step_iters > 8 || prm->sphere_tracing_iters < 0 ||
+      prm->sphere_tracing_iters > 64 || prm->n_secant_steps < 0 || prm->n_secant_steps > 16)
+    return fail(MVSDF_ERR_INVALID, "mvsdf_trace: iteration counts out of range");
+  if (training && !prm->skip_min_sdf && !steps01)
+    return fail(MVSDF_ERR_INVALID, "mvsdf_trace: steps01 is required in training mode (CPU-generator samples, ray_tracing.py:287)");
+  const int64_t R = (int64_t)n_images * n_pixels;
+  if (R <= 0 || R > (1ll << 30)) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: bad ray count");
+  if (workspace_bytes < mvsdf_trace_workspace_bytes(R, n_images))
+    return fail(MVSDF_ERR_WORKSPACE, "mvsdf_trace: workspace too small (%zu < %zu)", workspace_bytes,
+                mvsdf_trace_workspace_bytes(R, n_images));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WorkspaceLayout w = layout_for(R, n_images, 1 << 18);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  TraceCtx c{};
+  c.s.dir = out_ray_dirs;
+  float** fa[] = {&c.s.acc_s, &c.s.acc_e, &c.s.min_dis, &c.s.max_dis, &c.s.next_s, &c.s.next_e, &c.s.cur_s, &c.s.cur_e, &c.s.z};
+  for (int i = 0; i < 9; ++i) *fa[i] = reinterpret_cast<float*>(ws + w.off_f[i]);
+  c.s.slot_s = reinterpret_cast<int*>(ws + w.off_i[0]);
+  c.s.slot_e = reinterpret_cast<int*>(ws + w.off_i[1]);
+  c.s.list = reinterpret_cast<int*>(ws + w.off_i[2]);
+  c.s.list_pos = reinterpret_cast<int*>(ws + w.off_i[3]);
+  c.s.flags = reinterpret_cast<uint32_t*>(ws + w.off_flags);
+  float* tail = reinterpret_cast<float*>(ws + w.total);
+  c.s.z_lo = tail;
+  c.s.z_hi = tail + R;
+  c.s.f_lo = tail + 2 * R;
+  c.s.f_hi = tail + 3 * R;
+  float* cam = out_cam_loc ? out_cam_loc : reinterpret_cast<float*>(ws + w.off_cam);
+  c.cam = cam;
+  c.req_pts = reinterpret_cast<float*>(ws + w.off_req_pts);
+  c.req_val = reinterpret_cast<float*>(ws + w.off_req_val);
+  c.counters = reinterpret_cast<int*>(ws + w.off_counters);
+  c.R = (int)R;
+  c.N = n_pixels;
+  c.cap = w.cap;
+  c.thr = prm->sdf_threshold;
+  c.clip = prm->dist_clip;
+  c.line_step = prm->line_search_step;
+
+  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, kNumCounters * 4, st), "memset counters");
+  if (rc) return rc;
+  const int grid_r = (int)((R + kBlock - 1) / kBlock);
+  int ctr = 0;   // every request phase uses its own counter: no resets, no host round trips
+  auto eval = [&](int counter) {
+    return mlp_sdf(net, packed, c.req_pts, 0, c.counters + counter, MVSDF_HEAD_SDF_ONLY, c.req_val, nullptr, nullptr,
+                   false, st);
+  };
+  ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr);
+  if ((rc = eval(ctr++))) return rc;
+  for (int it = 0; it < prm->sphere_tracing_iters; ++it) {
+    trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr);
+    if ((rc = eval(ctr++))) return rc;
+    for (int k = 0; k < prm->line_step_iters; ++k) {
+      trace_backoff_kernel<<<grid_r, kBlock, 0, st>>>(c, k, ctr);
+      if ((rc = eval(ctr++))) return rc;
+    }
+  }
+  trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr);
+  const int list_ctr = ctr++;
+  trace_finish_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr);
+  // sampler in batches of batch_rays rays (worst case: every ray unconverged)
+  const int n_batches = (int)((R + w.batch_rays - 1) / w.batch_rays);
+  for (int b = 0; b < n_batches; ++b) {
+    const int begin = b * w.batch_rays;
+    const long long items = (long long)w.batch_rays * kSteps;
+    sampler_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, linspace100, list_ctr, begin,
+                                                                                w.batch_rays, ctr);
+    if ((rc = eval(ctr))) return rc;
+    sampler_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, linspace100, object_mask, training,
+                                                                                   list_ctr, begin, w.batch_rays);
+    ctr++;
+    if (ctr >= kNumCounters - 24) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many sampler batches");
+  }
+  for (int i = 0; i <= prm->n_secant_steps; ++i) {
+    const int push = i < prm->n_secant_steps;
+    secant_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr, i > 0, push, ctr);
+    if (push) {
+      if ((rc = eval(ctr++))) return rc;
+    }
+  }
+  if (training) {
+    const int ml_ctr = ctr++;
+    minsdf_prepare_kernel<<<grid_r, kBlock, 0, st>>>(c, object_mask, ml_ctr);
+    if (!prm->skip_min_sdf) {
+      for (int b = 0; b < n_batches; ++b) {
+        const int begin = b * w.batch_rays;
+        const long long items = (long long)w.batch_rays * kSteps;
+        minsdf_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
+                                                                                   w.batch_rays, ctr);
+        if ((rc = eval(ctr))) return rc;
+        minsdf_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
+                                                                                      w.batch_rays);
+        ctr++;
+        if (ctr >= kNumCounters - 2) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many min-sdf batches");
+      }
+    }
+  }
+  trace_output_kernel<<<grid_r, kBlock, 0, st>>>(c, out_dists, out_net_mask, out_points);
+  if (out_counters)
+    rc = check_cuda(cudaMemcpyAsync(out_counters, c.counters, kNumCounters * 4, cudaMemcpyDeviceToDevice, st),
+                    "copy counters");
+  if (rc) return rc;
+  return check_cuda(cudaGetLastError(), "mvsdf_trace launches");
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference's model interface for the hot path.
+
+``B200IDRNetwork`` keeps ``IDRNetwork``'s constructor argument (a pyhocon-like ``model`` config),
+parameter names (``implicit_network.lin{l}.{bias,weight_g,weight_v}``,
+``rendering_network.lin{l}.*`` -- released checkpoints load unchanged), the
+``forward(input, train_progress) -> dict`` signature and the output-dict keys of
+code/model/implicit_differentiable_renderer.py:179-322, but every stage runs in
+libmvsdf_b200.so (hand-written sm_100a CUDA behind the C ABI of include/mvsdf_b200.h).
+PyTorch only owns the device buffers and the stream.
+
+Scope of this round: the forward path.  Outputs are plain tensors without an
+autograd graph; the fused backward and the phase-0 depth-surface
+samples (row f2, train_progress < 1/6) are not built yet and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+import os
+from ctypes import byref, c_void_p
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _lib, conf as default_schedule, ops
+from .synth import FEATURE_SIZE
+
+
+class Conf:
+    """dict-backed stand-in for the pyhocon ConfigTree the reference passes to IDRNetwork
+    (get_int / get_float / get_config / get_list); real pyhocon objects work as well."""
+
+    def __init__(self, d):
+        self._d = d
+
+    def _get(self, key):
+        node = self._d
+        for part in key.split("."):
+            node = node[part]
+        return node
+
+    def get_int(self, key):
+        return int(self._get(key))
+
+    def get_float(self, key):
+        return float(self._get(key))
+
+    def get_list(self, key):
+        return list(self._get(key))
+
+    def get_string(self, key):
+        return str(self._get(key))
+
+    def get_config(self, key):
+        return Conf(self._get(key))
+
+    def keys(self):
+        return self._d.keys()
+
+    def __getitem__(self, k):
+        v = self._d[k]
+        return Conf(v) if isinstance(v, dict) else v
+
+
+def default_conf(width: int = 512, render_width: Optional[int] = None) -> Conf:
+    """The ``model{}`` block of code/confs/mvsdf_dtu.conf:17-58."""
+    rw = width if render_width is None else render_width
+    return Conf({
+        "feature_vector_size": FEATURE_SIZE,
+        "implicit_network": {"d_in": 3, "d_out": 1, "dims": [width] * 8, "geometric_init": True, "bias": 0.6,
+                             "skip_in": [4], "weight_norm": True, "multires": 6},
+        "rendering_network": {"mode": "idr", "d_in": 9, "d_out": 3, "dims": [rw] * 4, "weight_norm": True,
+                              "multires_view": 4},
+        "ray_tracer": {"object_bounding_sphere": 1.0, "sdf_threshold": 5.0e-5, "line_search_step": 0.5,
+                       "line_step_iters": 3, "sphere_tracing_iters": 10, "n_steps": 100, "n_secant_steps": 8},
+    })
+
+
+def _cfg(conf, key, default=None):
+    try:
+        return conf[key]
+    except Exception:
+        return default
+
+
+class WNLinear(nn.Module):
+    """Parameter holder with the names nn.utils.weight_norm(nn.Linear) produces
+    (bias, weight_g [out,1], weight_v [out,in]); the fold W = g v/||v|| happens on the device in
+    mvsdf_pack_weights."""
+
+    def __init__(self, in_dim: int, out_dim: int):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(out_dim))
+        self.weight_g = nn.Parameter(torch.ones(out_dim, 1))
+        self.weight_v = nn.Parameter(torch.zeros(out_dim, in_dim))
+
+    @torch.no_grad()
+    def set_weight(self, w: torch.Tensor, b: torch.Tensor):
+        self.weight_v.copy_(w)
+        self.weight_g.copy_(w.norm(dim=1, keepdim=True))
+        self.bias.copy_(b)
+
+
+class _PackedMlp(nn.Module):
+    kind = "sdf"
+
+    def _layers(self):
+        return [getattr(self, f"lin{l}") for l in range(self.num_layers - 1)]
+
+    def packed(self) -> ops.PackedNet:
+        """Folds weight-norm and re-packs the fp16 hi/lo tiles (cheap; done once per forward because the
+        optimiser changes the weights every step)."""
+        lins = self._layers()
+        dev = lins[0].weight_v.device
+        if dev.type != "cuda":
+            raise _lib.MvsdfError("mvsdf_b200 runs on CUDA devices only (no CPU fallback); move the module to cuda")
+        if self._net is None:
+            self._net = self._make_plan()
+        self._net.pack([l.weight_v for l in lins], [l.weight_g for l in lins], [l.bias for l in lins])
+        return self._net
+
+
+class ImplicitNetwork(_PackedMlp):
+    """SDF MLP (implicit_differentiable_renderer.py:19-107): parameters + kernel-backed forward/gradient."""
+
+    def __init__(self, feature_vector_size, d_in, d_out, dims, geometric_init=True, bias=1.0, skip_in=(),
+                 weight_norm=True, multires=0):
+        super().__init__()
+        dims = list(dims)
+        if d_in != 3 or d_out != 1 or multires != 6 or not weight_norm or len(set(dims)) != 1 or len(skip_in) != 1:
+            raise _lib.MvsdfError("mvsdf_b200 supports the shipped SDF architecture family: d_in=3, d_out=1, "
+                                  "multires=6, equal hidden widths, one skip layer, weight_norm=True")
+        self.width = dims[0]
+        self.n_hidden = len(dims)
+        self.feature_vector_size = feature_vector_size
+        self.skip_in = tuple(skip_in)
+        self.d0 = 3 + 6 * multires
+        full = [self.d0] + dims + [d_out + 1 + feature_vector_size]
+        self.num_layers = len(full)
+        for l in range(self.num_layers - 1):
+            out_dim = full[l + 1] - full[0] if (l + 1) in self.skip_in else full[l + 1]
+            lin = WNLinear(full[l], out_dim)
+            if geometric_init:       # :53-68
+                with torch.no_grad():
+                    if l == self.num_layers - 2:
+                        w = torch.empty(out_dim, full[l]).normal_(math.sqrt(math.pi) / math.sqrt(full[l]), 0.0001)
+                        b = torch.full((out_dim,), -float(bias))
+                    elif l == 0:
+                        w = torch.zeros(out_dim, full[l])
+                        w[:, :3].normal_(0.0, math.sqrt(2) / math.sqrt(out_dim))
+                        b = torch.zeros(out_dim)
+                    elif l in self.skip_in:
+                        w = torch.empty(out_dim, full[l]).normal_(0.0, math.sqrt(2) / math.sqrt(out_dim))
+                        w[:, -(full[0] - 3):] = 0.0
+                        b = torch.zeros(out_dim)
+                    else:
+                        w = torch.empty(out_dim, full[l]).normal_(0.0, math.sqrt(2) / math.sqrt(out_dim))
+                        b = torch.zeros(out_dim)
+                    lin.set_weight(w, b)
+            else:
+                with torch.no_grad():
+                    bound = 1.0 / math.sqrt(full[l])
+                    lin.set_weight(torch.empty(out_dim, full[l]).uniform_(-bound, bound),
+                                   torch.empty(out_dim).uniform_(-bound, bound))
+            setattr(self, "lin" + str(l), lin)
+        self._net: Optional[ops.PackedNet] = None
+
+    def _make_plan(self):
+        return ops.PackedNet("sdf", self.width, self.n_hidden, self.feature_vector_size, self.skip_in[0], 6)
+
+    @torch.no_grad()
+    def forward(self, input, compute_grad=False):
+        """[P,3] -> [P, 2+F] (column 0 SDF, 1 surface indicator, 2: features); forward values only."""
+        return ops.sdf_forward(self.packed(), input, ops.HEAD_FULL)
+
+    @torch.no_grad()
+    def gradient(self, x):
+        """[P,3] -> [P,1,3] (:96-107), computed by forward-mode tangents in the fused kernel."""
+        _, g = ops.sdf_value_grad(self.packed(), x, ops.HEAD_SDF_ONLY)
+        return g.unsqueeze(1)
+
+
+class RenderingNetwork(_PackedMlp):
+    """Surface light field MLP (implicit_differentiable_renderer.py:109-167), mode='idr'."""
+
+    def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, multires_view=0):
+        super().__init__()
+        dims = list(dims)
+        if mode != "idr" or d_in != 9 or d_out != 3 or multires_view != 4 or not weight_norm or len(set(dims)) != 1:
+            raise _lib.MvsdfError("mvsdf_b200 supports the shipped rendering net: mode='idr', d_in=9, d_out=3, "
+                                  "multires_view=4, equal hidden widths, weight_norm=True")
+        self.mode = mode
+        self.width = dims[0]
+        self.n_hidden = len(dims)
+        self.feature_vector_size = feature_vector_size
+        full = [d_in + feature_vector_size + 6 * multires_view] + dims + [d_out]
+        self.num_layers = len(full)
+        for l in range(self.num_layers - 1):
+            lin = WNLinear(full[l], full[l + 1])
+            with torch.no_grad():
+                bound = 1.0 / math.sqrt(full[l])
+                lin.set_weight(torch.empty(full[l + 1], full[l]).uniform_(-bound, bound),
+                               torch.empty(full[l + 1]).uniform_(-bound, bound))
+            setattr(self, "lin" + str(l), lin)
+        self._net: Optional[ops.PackedNet] = None
+
+    def _make_plan(self):
+        return ops.PackedNet("render", self.width, self.n_hidden, self.feature_vector_size, n_freqs=4)
+
+    @torch.no_grad()
+    def forward(self, points, normals, view_dirs, feature_vectors):
+        return ops.render_forward(self.packed(), points, view_dirs, normals, feature_vectors)
+
+
+class B200IDRNetwork(nn.Module):
+    """Drop-in for IDRNetwork on the forward path (see module docstring)."""
+
+    def __init__(self, conf, schedule=None):
+        super().__init__()
+        self.feature_vector_size = conf.get_int("feature_vector_size")
+        self.implicit_network = ImplicitNetwork(self.feature_vector_size, **conf.get_config("implicit_network"))
+        self.rendering_network = RenderingNetwork(self.feature_vector_size, **conf.get_config("rendering_network"))
+        rt = conf.get_config("ray_tracer")
+        self.tracer_conf = {
+            "object_bounding_sphere": float(_cfg(rt, "object_bounding_sphere", 1.0)),
+            "sdf_threshold": float(_cfg(rt, "sdf_threshold", 5.0e-5)),
+            "line_search_step": float(_cfg(rt, "line_search_step", 0.5)),
+            "line_step_iters": int(_cfg(rt, "line_step_iters", 1)),
+            "sphere_tracing_iters": int(_cfg(rt, "sphere_tracing_iters", 10)),
+            "n_steps": int(_cfg(rt, "n_steps", 100)),
+            "n_secant_steps": int(_cfg(rt, "n_secant_steps", 8)),
+        }
+        self.object_bounding_sphere = self.tracer_conf["object_bounding_sphere"]
+        self.schedule = schedule if schedule is not None else default_schedule
+        self.skip_min_sdf = False          # minimal_sdf_points feeds no MVSDF loss; keep for parity
+        self._ws: Dict[str, torch.Tensor] = {}
+        self.last_trace_counters: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name: str, nbytes: int, device) -> torch.Tensor:
+        t = self._ws.get(name)
+        if t is None or t.numel() < nbytes or t.device != device:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[name] = t
+        return t
+
+    def _tracer_params(self, L):
+        p = L.TracerParams()
+        c = self.tracer_conf
+        p.object_bounding_sphere = c["object_bounding_sphere"]
+        p.sdf_threshold = c["sdf_threshold"]
+        p.line_search_step = c["line_search_step"]
+        p.dist_clip = 0.5                       # ray_tracing.py:131
+        p.line_step_iters = c["line_step_iters"]
+        p.sphere_tracing_iters = c["sphere_tracing_iters"]
+        if os.environ.get("IDR_USE_ENV", "0") == "1" and os.environ.get("IDR_RENDER", "0") == "1":
+            p.dist_clip = 0.05                  # ray_tracing.py:127-129
+            p.sphere_tracing_iters = 40
+        p.n_steps = c["n_steps"]
+        p.n_secant_steps = c["n_secant_steps"]
+        p.skip_min_sdf = 1 if self.skip_min_sdf else 0
+        return p
+
+    def trace(self, sdf_net, uv, pose, intrinsics, object_mask_u8, training: bool, steps01=None):
+        """RayTracing.forward through mvsdf_trace.  Returns ray_dirs [R,3], cam_loc [B,3], dists [R],
+        network_object_mask [R] bool, points [R,3]."""
+        L = _lib.lib()
+        dev = uv.device
+        B, N, _ = uv.shape
+        R = B * N
+        ws = self._buf("trace", L.mvsdf_trace_workspace_bytes(R, B), dev)
+        f = dict(dtype=torch.float32, device=dev)
+        ray_dirs = torch.empty(R, 3, **f)
+        cam_loc = torch.empty(B, 3, **f)
+        dists = torch.empty(R, **f)
+        net_mask = torch.empty(R, dtype=torch.uint8, device=dev)
+        points = torch.empty(R, 3, **f)
+        counters = torch.empty(128, dtype=torch.int32, device=dev)
+        lin = torch.linspace(0, 1, steps=self.tracer_conf["n_steps"]).to(dev)        # ray_tracing.py:206
+        steps = None
+        if training and not self.skip_min_sdf:
+            # same draw as ray_tracing.py:287: CPU default generator, then moved to the device
+            steps = (steps01 if steps01 is not None else torch.empty(self.tracer_conf["n_steps"]).uniform_(0.0, 1.0))
+            steps = steps.to(device=dev, dtype=torch.float32).contiguous()
+        prm = self._tracer_params(L)
+        _lib.check(L.mvsdf_trace(sdf_net.handle, _lib.ptr(sdf_net.blob), _lib.ptr(uv), _lib.ptr(pose), _lib.ptr(intrinsics),
+                                 _lib.ptr(object_mask_u8), byref(prm), B, N, 1 if training else 0, _lib.ptr(lin),
+                                 _lib.ptr(steps), ws.numel(), _lib.ptr(ws), _lib.ptr(ray_dirs), _lib.ptr(cam_loc),
+                                 _lib.ptr(dists), _lib.ptr(net_mask), _lib.ptr(points), _lib.ptr(counters),
+                                 c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        self.last_trace_counters = counters
+        return ray_dirs, cam_loc, dists, net_mask, points
+
+    # ------------------------------------------------------------------ IDRNetwork.forward
+    @torch.no_grad()
+    def forward(self, input, train_progress=None, steps01=None, eik_points=None):
+        L = _lib.lib()
+        conf = self.schedule
+        uv = ops._f32(input["uv"])
+        pose = ops._f32(input["pose"])
+        intrinsics = ops._f32(input["intrinsics"])
+        dev = uv.device
+        object_mask_true = input["object_mask"].reshape(-1).to(device=dev, dtype=torch.bool)
+        object_mask = object_mask_true if conf.use_mask else torch.ones_like(object_mask_true)
+        if pose.shape[1] == 7:
+            raise NotImplementedError("quaternion poses (train_cameras=True) are outside the hot path")
+        B, N, _ = uv.shape
+        R = B * N
+        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+        sdf_net = self.implicit_network.packed()
+        rend_net = self.rendering_network.packed()
+        obj_u8 = object_mask.to(torch.uint8).contiguous()
+        training = self.training
+        if training:
+            assert train_progress is not None
+            if any([conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
+                    conf.eik_use_dsurf_on(train_progress), conf.eik_use_dsurf_jitter(train_progress)]):
+                raise NotImplementedError("depth-surface samples (train_progress < 1/6, "
+                                          "implicit_differentiable_renderer.py:226-251) are SURVEY section 8 row f2")
+        ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics, obj_u8, training, steps01)
+        network_object_mask = net_u8.bool()
+        surface_u8 = (net_u8 & obj_u8) if training else net_u8
+
+        f = dict(dtype=torch.float32, device=dev)
+        sdf_out = torch.empty(R, **f)
+        rgb_values = torch.empty(R, 3, **f)
+        surf_pts = torch.empty(R, 3, **f)
+        normals = torch.empty(R, 3, **f)
+        surf_head = torch.empty(R, 2, **f)
+        hit_index = torch.empty(R, dtype=torch.int32, device=dev)
+        hit_offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        F = self.feature_vector_size
+        ws = self._buf("shade", L.mvsdf_shade_workspace_bytes(R, F), dev)
+        _lib.check(L.mvsdf_shade_rays(sdf_net.handle, _lib.ptr(sdf_net.blob), rend_net.handle, _lib.ptr(rend_net.blob),
+                                      _lib.ptr(ray_dirs), _lib.ptr(points), _lib.ptr(surface_u8), B, N, F, ws.numel(),
+                                      _lib.ptr(ws), _lib.ptr(sdf_out), _lib.ptr(rgb_values), _lib.ptr(surf_pts),
+                                      _lib.ptr(normals), _lib.ptr(surf_head), _lib.ptr(hit_index), _lib.ptr(hit_offsets),
+                                      stream))
+        M = int(hit_offsets[B].item())          # the single host sync: diff_surf_pts has a data-dependent shape
+        diff_surf_pts = surf_pts[:M]
+        output = {
+            "points": points,
+            "diff_surf_pts": diff_surf_pts,
+            "rgb_values": rgb_values,
+            "sdf_output": sdf_out.unsqueeze(1),
+            "network_object_mask": network_object_mask,
+            "object_mask": object_mask,
+            "object_mask_true": object_mask_true,
+            "grad_theta": None,
+            # extras (not in the reference dict) consumed by B200IDRLoss to skip recomputation
+            "hit_offsets": hit_offsets,
+            "surface_normals": normals[:M],
+            "ray_dirs": ray_dirs,
+            "dists": dists,
+        }
+        if training:
+            n_eik = R // 2
+            if eik_points is None:
+                r = self.object_bounding_sphere      # :216-221, CPU generator then .cuda()
+                eik_points = torch.empty(n_eik, 3).uniform_(-r, r)
+            eik_points = eik_points.to(device=dev, dtype=torch.float32).contiguous()
+            extra, g_eik = ops.sdf_value_grad(sdf_net, eik_points, ops.HEAD_FULL)
+            f_s = surf_head[:M, 0:1]
+            eik_pts = torch.cat([diff_surf_pts, eik_points], dim=0)
+            output["eikonal_output"] = torch.cat([f_s, extra[:, :1]], dim=0).view(1, -1)
+            output["eikonal_points_hom"] = torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1)
+            keep = object_mask_true[hit_index[:M].long()]
+            output["surf_indicator_output"] = torch.cat([surf_head[:M, 1][keep], extra[:, 1]], dim=0)
+            output["grad_theta"] = torch.cat([normals[:M], g_eik], dim=0)
+        return output

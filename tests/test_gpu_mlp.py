@@ -8,7 +8,7 @@ from tests.helpers import preset_state_dict, t
 
 pytestmark = pytest.mark.gpu
 
-TOL_SDF = 2e-5      # absolute, on O(1) SDF values: well inside the 1e-4 relative gate on depths
+TOL_SDF = 5e-5      # absolute, on O(1) SDF values (tensor-core fp32 accumulation truncates): inside the 1e-4 relative depth gate
 TOL_GRAD = 1e-4
 TOL_RGB = 1e-4
 
