@@ -159,6 +159,7 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,
             float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st) {
   if (!net || net->plan.kind != NET_SDF) return fail(MVSDF_ERR_INVALID, "expected an SDF net plan");
+  if (n == 0 && !n_dev) return MVSDF_OK;   // empty batch: nothing to enqueue
   if (!packed || (!x && n > 0) || n < 0) return fail(MVSDF_ERR_INVALID, "null pointer / negative count");
   if (head != HEAD_SDF_ONLY && head != HEAD_FULL) return fail(MVSDF_ERR_INVALID, "bad head %d", head);
   if (head == HEAD_SDF_ONLY && !out_sdf) return fail(MVSDF_ERR_INVALID, "out_sdf is required for the SDF-only head");
@@ -176,6 +177,7 @@ int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n,
 int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const float* view, const float* normals,
                const float* feats, int feat_stride, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st) {
   if (!net || net->plan.kind != NET_RENDER) return fail(MVSDF_ERR_INVALID, "expected a rendering net plan");
+  if (n == 0 && !n_dev) return MVSDF_OK;
   if (!packed || n < 0 || !rgb || ((!pts || !view || !normals || !feats) && n > 0))
     return fail(MVSDF_ERR_INVALID, "null pointer / negative count");
   MlpArgs a;
