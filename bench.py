@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the MVSDF hot path (sphere-trace + render + feature loss + rgb L1).
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line
+(rank 0).  A "step" is one eval-mode pass of the hot path over one batch of synthetic rays:
+IDRNetwork.forward + get_feat_loss_corr + get_rgb_loss.
+
+Workloads (BASELINE.json `configs`):
+  cfg2 (default, the configuration the metric is quoted on): DTU-shaped 1200x1600 full image =
+       1.92 M rays, 4 source views, 8x512 SDF MLP + 4x512 rendering MLP, eval mode, one image per GPU
+       (weak scaling: every rank renders its own view of the scene; loss partials are all-reduced).
+  cfg3: 2 x 4096 rays, 8 source views, train-mode forward (tp = 0.5).
+  cfg1: 32x32 rays, 256-wide nets, 1 source view (the CPU-runnable case).
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port in
+oracle/mvsdf_oracle.py, pinned against the unmodified reference by tests/golden) on the host cores,
+each step a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mvsdf_b200 import synth  # noqa: E402
+
+METRIC = "rays/sec (sphere-trace+render+feat-loss) at DTU 1200x1600"
+
+WORKLOADS = {
+    "cfg2": dict(H=1200, W=1600, width=512, n_src=4, n_images=1, n_rays=None, training=False,
+                 weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
+    "cfg3": dict(H=1200, W=1600, width=512, n_src=8, n_images=2, n_rays=4096, training=True,
+                 weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
+    "cfg1": dict(H=32, W=32, width=256, n_src=1, n_images=1, n_rays=None, training=False,
+                 weights=dict(width=256, seed=1, perturb=0.05, pe_noise=0.003, bias=0.6)),
+}
+
+# algorithmic FLOPs per SDF evaluation / shaded ray
+FLOP = {512: dict(sdf_only=3.671e6, full=3.934e6, render=1.872e6), 256: dict(sdf_only=0.918e6, full=1.050e6, render=0.543e6)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d.get("bf16_tflops"), bf16_sustained=d.get("bf16_tflops_sustained"), hbm=d.get("hbm_gbs"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_inputs(cfg, rank):
+    """Host (pinned) tensors of one step. Every rank renders a different view of the same synthetic scene."""
+    scene = synth.make_scene(cfg["H"], cfg["W"], n_images=cfg["n_images"], n_src=cfg["n_src"], n_rays=cfg["n_rays"],
+                             seed=rank)
+    sd = synth.make_state_dict(**cfg["weights"])
+    return scene, sd
+
+
+def pin(d):
+    return {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+IN_KEYS = ["uv", "pose", "intrinsics", "object_mask"]
+GT_KEYS = ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center"]
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from mvsdf_b200 import _lib
+    from mvsdf_b200.loss import B200IDRLoss
+    from mvsdf_b200.network import B200IDRNetwork, default_conf
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = WORKLOADS[args.workload]
+    scene, sd = make_inputs(cfg, rank)
+    B, N = scene["uv"].shape[:2]
+    R = B * N
+    model = B200IDRNetwork(default_conf(cfg["width"])).to(dev)
+    model.load_state_dict(sd)
+    model.train(cfg["training"])
+    model.skip_min_sdf = bool(args.skip_min_sdf)
+    loss_mod = B200IDRLoss()
+    L = _lib.lib()
+    tp = 0.5
+    g = torch.Generator().manual_seed(1234 + rank)
+    steps01 = torch.rand(100, generator=g)
+    eik = (torch.rand(R // 2, 3, generator=g) * 2 - 1)
+
+    def reduce_fn(partial):
+        if world > 1:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM)     # the single NCCL collective of the path
+
+    host = pin({k: scene[k] for k in IN_KEYS + GT_KEYS})
+    resident = {k: host[k].to(dev) for k in IN_KEYS + GT_KEYS}
+
+    def step(inputs):
+        kw = dict(steps01=steps01, eik_points=eik) if cfg["training"] else {}
+        out = model({k: inputs[k] for k in IN_KEYS}, tp if cfg["training"] else None, **kw)
+        losses = loss_mod.hot_path_losses(out, {k: inputs[k] for k in GT_KEYS}, tp, reduce_fn=reduce_fn)
+        return out, losses
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident timing (`value`)
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = L.mvsdf_launch_count()
+    L.mvsdf_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out, losses = step(resident)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = L.mvsdf_launch_count() - launches0
+    import ctypes
+    ms_kind = (ctypes.c_float * 4)()
+    n_kind = (ctypes.c_int * 4)()
+    _lib.check(L.mvsdf_profile_collect(ms_kind, n_kind))
+    L.mvsdf_profile_enable(0)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * R / (ms_per_step * 1e-3)
+
+    # tracer evaluations of the last step (E_trace of SURVEY 8d: requests the reference algorithm issues)
+    evals = int(model.last_trace_counters.cpu().sum().item())
+    n_hit = int(out["hit_offsets"][-1].item())
+    width = cfg["width"]
+    fl = FLOP[width]
+    sdf_only_evals = evals + R                                   # + sdf_output for every ray
+    alg_flops_kernel = sdf_only_evals * fl["sdf_only"]            # per step, kernel kind 0
+    ms_kernel = ms_kind[0] / args.steps
+    peaks = load_peaks()
+    achieved = alg_flops_kernel / (ms_kernel * 1e-3) / 1e12 if ms_kernel > 0 else None
+    total_alg_flops = evals * fl["sdf_only"] + R * fl["sdf_only"] + n_hit * (3 * fl["full"] + fl["render"])
+    if cfg["training"]:
+        total_alg_flops += (R // 2) * 4 * fl["full"]
+
+    # ---------------- end-to-end through the public API with host buffers (`e2e`)
+    def h2d_step():
+        inputs = {k: host[k].to(dev, non_blocking=True) for k in IN_KEYS + GT_KEYS}
+        _, ls = step(inputs)
+        vals = torch.stack([ls["rgb_loss"].reshape(()), ls["feat_loss"].reshape(())]).cpu()   # D2H of the step's result
+        return vals
+
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in IN_KEYS + GT_KEYS)
+    d2h_bytes = 8 + 4 * (B + 1)          # the two loss scalars + the hit-count read inside forward()
+    for _ in range(max(1, args.warmup // 2)):
+        h2d_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        vals = h2d_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item()) / args.steps
+    e2e_value = world * R / (ms_e2e * 1e-3)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference_sample(cfg, scene, sd, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32-equivalent (fp16 hi/lo split operands, fp32 tensor-core accumulate)", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg['H']}x{cfg['W']} image, {R} rays/GPU, {cfg['n_src']} src views, "
+                                   f"8x{width} SDF MLP + 4x{width} render MLP, {'train' if cfg['training'] else 'eval'}-mode forward "
+                                   f"+ feat loss + rgb L1", "rays_per_gpu": R, "hit_fraction": n_hit / R,
+                       "tracer_evals_per_ray": evals / R, "parallelism": f"ray-sharded dp{world}, loss-partials all-reduce",
+                       "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
+                       "skip_min_sdf": bool(args.skip_min_sdf)},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "mlp_tile_kernel<NET_SDF, plain, SDF-only head>",
+                         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                         "algorithmic_flops_per_launch": alg_flops_kernel / max(1, n_kind[0] / args.steps),
+                         "launches_per_step": n_kind[0] / args.steps, "kernel_ms_per_step": ms_kernel,
+                         "kernel_share_of_step": ms_kernel / ms_per_step,
+                         "note": "algorithmic FLOPs = 2*MAC of the fp32 network; the kernel issues 3 fp16 UMMAs per MAC "
+                                 "(hi*hi + lo*hi + hi*lo), so tensor-pipe work is 3x the algorithmic figure"},
+            "step_algorithmic_tflop": total_alg_flops / 1e12,
+            "losses": {"rgb": float(vals[0]), "feat": float(vals[1])},
+            "mlp_ms_per_step_by_kind": {"sdf_only": ms_kind[0] / args.steps, "sdf_full": ms_kind[1] / args.steps,
+                                        "value_grad": ms_kind[2] / args.steps, "render": ms_kind[3] / args.steps},
+        }
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_sample(cfg, scene, sd, budget_s=20.0, threads=None):
+    """The oracle port of the reference algorithm on the host cores, on a bounded sample of the same workload:
+    a regular sub-grid of the image's rays (same cameras, weights, feature maps)."""
+    from oracle import mvsdf_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sw, rw = O.sdf_weights(sd), O.render_weights(sd)
+    N = scene["uv"].shape[1]
+    # calibrate: ~60 evals/ray * 2 * MACs at ~25 GFLOP/s/core-ish -> pick a sample, then rescale once
+    n_sample = min(N, 1024 if cfg["width"] >= 512 else 4096)
+    warm = dict(scene)
+    warm["uv"] = scene["uv"][:, :64].contiguous()
+    warm["object_mask"] = scene["object_mask"][:, :64].contiguous()
+    warm["rgb"] = scene["rgb"][:, :64].contiguous()
+    O.idr_forward(sw, rw, warm, None, False)          # thread-pool / allocator warm-up, not timed
+    while True:
+        stride = max(1, N // n_sample)
+        idx = torch.arange(0, N, stride)[:n_sample]
+        sub = dict(scene)
+        sub["uv"] = scene["uv"][:, idx].contiguous()
+        sub["object_mask"] = scene["object_mask"][:, idx].contiguous()
+        sub["rgb"] = scene["rgb"][:, idx].contiguous()
+        t0 = time.perf_counter()
+        out = O.idr_forward(sw, rw, sub, None, False)
+        O.hot_path_losses(out, sub, 0.5)
+        dt = time.perf_counter() - t0
+        n_done = sub["uv"].shape[0] * sub["uv"].shape[1]
+        if dt >= 0.4 * budget_s or n_sample >= N:
+            break
+        n_sample = int(min(N, n_sample * min(8.0, 0.8 * budget_s / max(dt, 1e-3))))
+    return {"value": n_done / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"{n_done} rays (regular sub-grid of the {cfg['H']}x{cfg['W']} image, same weights/cameras/features), "
+                      f"eval forward + feat loss + rgb L1 in {dt:.1f} s; oracle/mvsdf_oracle.py (PyTorch CPU restatement "
+                      "pinned to the reference by tests/golden)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = WORKLOADS[args.workload]
+    scene, sd = make_inputs(cfg, 0)
+    R = scene["uv"].shape[0] * scene["uv"].shape[1]
+    per_step_budget = max(5.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    res = None
+    t_all = []
+    for i in range(args.warmup + args.steps):
+        res = cpu_reference_sample(cfg, scene, sd, budget_s=per_step_budget)
+        if i >= args.warmup:
+            t_all.append(res["value"])
+    value = sum(t_all) / len(t_all)
+    res["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": R / value * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {cfg['H']}x{cfg['W']} image, {cfg['n_src']} src views, 8x{cfg['width']} SDF MLP + "
+                               f"4x{cfg['width']} render MLP, eval-mode forward + feat loss + rgb L1; CPU, bounded sample per step",
+                   "rays_per_gpu": R},
+        "cpu_baseline": res,
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is pure Python/PyTorch and cannot travel to the GPU box (no copying of reference sources); this arm "
+                "times oracle/mvsdf_oracle.py, the restatement pinned to the unmodified reference by tests/golden and "
+                "tests/test_oracle.py, on all host cores",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--skip-min-sdf", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

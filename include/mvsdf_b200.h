@@ -39,6 +39,12 @@ typedef struct mvsdf_net mvsdf_net;   /* host-side layout plan of one packed MLP
 
 int mvsdf_abi_version(void);
 const char* mvsdf_last_error(void);
+/* Instrumentation (no reference counterpart): cumulative number of CUDA kernels this library has launched, and
+ * optional CUDA-event timing of the MLP tile launches on their own stream (kinds: 0 SDF-only head, 1 full head,
+ * 2 value+gradient, 3 rendering net).  mvsdf_profile_collect synchronises on the recorded events. */
+long long mvsdf_launch_count(void);
+void mvsdf_profile_enable(int on);
+int mvsdf_profile_collect(float* ms_by_kind_host, int* launches_by_kind_host);
 
 /* ---- network plans ------------------------------------------------------------------------------
  * ImplicitNetwork.__init__ (implicit_differentiable_renderer.py:19-75): dims [3+6*n_freqs] + [width]*n_hidden

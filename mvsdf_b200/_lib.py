@@ -23,6 +23,11 @@ def _declare(lib):
     P = c_void_p
     lib.mvsdf_abi_version.restype = c_int
     lib.mvsdf_last_error.restype = c_char_p
+    lib.mvsdf_launch_count.restype = ctypes.c_longlong
+    lib.mvsdf_profile_enable.restype = None
+    lib.mvsdf_profile_enable.argtypes = [c_int]
+    lib.mvsdf_profile_collect.restype = c_int
+    lib.mvsdf_profile_collect.argtypes = [POINTER(c_float), POINTER(c_int)]
     lib.mvsdf_sdf_net_create.restype = P
     lib.mvsdf_sdf_net_create.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.mvsdf_render_net_create.restype = P

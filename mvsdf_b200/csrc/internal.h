@@ -12,6 +12,7 @@ namespace mvsdf {
 int fail(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int sm_count();
+void note_launch();   // counts kernel launches made by the library (mvsdf_launch_count)
 
 // MLP tile launches (mlp_abi.cu)
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,

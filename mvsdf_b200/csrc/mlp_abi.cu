@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/mvsdf_b200.h"
 #include "internal.h"
@@ -44,6 +45,31 @@ int sm_count() {
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static long long g_launches = 0;
+void note_launch() { ++g_launches; }
+
+// Optional per-launch timing of the MLP tile kernels with CUDA events on the launching stream
+// (bench.py's roofline leg). kinds: 0 SDF plain / SDF-only head, 1 SDF plain / full head, 2 SDF value+grad, 3 render.
+struct ProfEvent { cudaEvent_t e0, e1; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_pool;
+static size_t g_prof_used = 0;
+static ProfEvent* prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on) return nullptr;
+  if (g_prof_used == g_prof_pool.size()) {
+    ProfEvent p{};
+    if (cudaEventCreate(&p.e0) != cudaSuccess || cudaEventCreate(&p.e1) != cudaSuccess) return nullptr;
+    g_prof_pool.push_back(p);
+  }
+  ProfEvent* p = &g_prof_pool[g_prof_used++];
+  p->kind = kind;
+  cudaEventRecord(p->e0, st);
+  return p;
+}
+static void prof_end(ProfEvent* p, cudaStream_t st) {
+  if (p) cudaEventRecord(p->e1, st);
+}
 
 static void finalize_plan(NetPlan& p) {
   long long off = 0;
@@ -152,7 +178,10 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(mlp_tile_kernel)");
   if (rc) return rc;
-  kern<<<grid, kMlpThreads, smem, st>>>(a);
+  const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : 0));
+  ProfEvent* pe = prof_begin(kind, st);
+  note_launch(); kern<<<grid, kMlpThreads, smem, st>>>(a);
+  prof_end(pe, st);
   return check_cuda(cudaGetLastError(), "launch mlp_tile_kernel");
 }
 
@@ -198,6 +227,29 @@ using namespace mvsdf;
 extern "C" {
 
 int mvsdf_abi_version(void) { return 1; }
+long long mvsdf_launch_count(void) { return g_launches; }
+void mvsdf_profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+}
+int mvsdf_profile_collect(float* ms_by_kind, int* launches_by_kind) {
+  if (!ms_by_kind || !launches_by_kind) return fail(MVSDF_ERR_INVALID, "mvsdf_profile_collect: null argument");
+  for (int k = 0; k < 4; ++k) {
+    ms_by_kind[k] = 0.f;
+    launches_by_kind[k] = 0;
+  }
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    ProfEvent& p = g_prof_pool[i];
+    int rc = check_cuda(cudaEventSynchronize(p.e1), "profile event sync");
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    ms_by_kind[p.kind] += ms;
+    launches_by_kind[p.kind] += 1;
+  }
+  g_prof_used = 0;
+  return MVSDF_OK;
+}
 const char* mvsdf_last_error(void) { return g_err; }
 
 mvsdf_net* mvsdf_sdf_net_create(int width, int n_hidden, int skip_layer, int n_freqs, int feature_size) {
@@ -311,12 +363,12 @@ int mvsdf_pack_weights(const mvsdf_net* net, const float* const* weight_v_host, 
       }
     if (!weight_v_host[s] || !bias_host[s]) return fail(MVSDF_ERR_INVALID, "null weight pointer for layer %d", s);
     const float* g = weight_g_host ? weight_g_host[s] : nullptr;
-    row_scale_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(weight_v_host[s], g, rows, cols, scale + p.scale_off[s]);
+    note_launch(); row_scale_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(weight_v_host[s], g, rows, cols, scale + p.scale_off[s]);
   }
   for (int i = 0; i < p.n_layers; ++i) {
     const LayerPlan& L = p.L[i];
     const int total = L.m_tiles * kTileM * L.k_chunks * (kChunkK / 8);
-    pack_layer_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight_v_host[L.src_layer], scale + p.scale_off[L.src_layer],
+    note_launch(); pack_layer_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight_v_host[L.src_layer], scale + p.scale_off[L.src_layer],
                                                             bias_host[L.src_layer], L, p.feat_size, blob, bias_dst);
   }
   return check_cuda(cudaGetLastError(), "pack_weights launch");

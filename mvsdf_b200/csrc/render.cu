@@ -367,12 +367,12 @@ int mvsdf_shade_rays(const mvsdf_net* sdf_net, const void* sdf_packed, const mvs
   if (out_sdf && (rc = mlp_sdf(sdf_net, sdf_packed, points, R, nullptr, MVSDF_HEAD_SDF_ONLY, out_sdf, nullptr, nullptr,
                                false, st)))
     return rc;
-  hit_count_kernel<<<l.n_blocks, kBlk, 0, st>>>(surface_mask, (int)R, block_counts);
-  hit_scan_kernel<<<1, 1024, 0, st>>>(block_counts, l.n_blocks, n_images, n_pixels, surface_mask, out_hit_offsets,
+  note_launch(); hit_count_kernel<<<l.n_blocks, kBlk, 0, st>>>(surface_mask, (int)R, block_counts);
+  note_launch(); hit_scan_kernel<<<1, 1024, 0, st>>>(block_counts, l.n_blocks, n_images, n_pixels, surface_mask, out_hit_offsets,
                                       chunk_counts, l.n_chunks);
-  hit_scatter_kernel<<<l.n_blocks, kBlk, 0, st>>>(surface_mask, (int)R, n_pixels, block_counts, points, ray_dirs,
+  note_launch(); hit_scatter_kernel<<<l.n_blocks, kBlk, 0, st>>>(surface_mask, (int)R, n_pixels, block_counts, points, ray_dirs,
                                                   out_hit_index, out_surf_pts, view_hit);
-  fill_ones_kernel<<<(int)((3 * R + kBlk - 1) / kBlk), kBlk, 0, st>>>(out_rgb_values, 3 * R);
+  note_launch(); fill_ones_kernel<<<(int)((3 * R + kBlk - 1) / kBlk), kBlk, 0, st>>>(out_rgb_values, 3 * R);
   const int stride = feature_size + 2;
   for (int c = 0; c < l.n_chunks; ++c) {
     const size_t begin = (size_t)c * kHitChunk;
@@ -384,7 +384,7 @@ int mvsdf_shade_rays(const mvsdf_net* sdf_net, const void* sdf_packed, const mvs
                          out_normals + 3 * begin, full + 2, stride, 0, chunk_counts + c, rgb_hit + 3 * begin, st)))
       return rc;
     const int64_t cap = std::min<int64_t>(R - (int64_t)begin, kHitChunk);
-    shade_scatter_kernel<<<(int)((cap + kBlk - 1) / kBlk), kBlk, 0, st>>>(chunk_counts + c, (int)begin, out_hit_index,
+    note_launch(); shade_scatter_kernel<<<(int)((cap + kBlk - 1) / kBlk), kBlk, 0, st>>>(chunk_counts + c, (int)begin, out_hit_index,
                                                                           rgb_hit, full, stride, out_rgb_values,
                                                                           out_surf_head);
   }
@@ -396,7 +396,7 @@ int mvsdf_feat_nchw_to_nhwc(const float* src, int n, int channels, int h, int w,
     return fail(MVSDF_ERR_INVALID, "mvsdf_feat_nchw_to_nhwc: bad argument (channels must be <= 32)");
   const int hw = h * w;
   dim3 grid((hw + 31) / 32, n);
-  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, channels, hw, dst);
+  note_launch(); nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, channels, hw, dst);
   return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
 }
 
@@ -413,14 +413,14 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
   FeatArgs a{surf_pts, hit_offsets, cams, maps_nhwc, size, center, partials, n_images, n_views, h, w};
   const int sms = sm_count();
   if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
-  feat_counts_kernel<<<(n_images + 63) / 64, 64, 0, st>>>(hit_offsets, n_images, n_views, partials);
-  feat_loss_kernel<<<sms * 8, 256, 0, st>>>(a);
+  note_launch(); feat_counts_kernel<<<(n_images + 63) / 64, 64, 0, st>>>(hit_offsets, n_images, n_views, partials);
+  note_launch(); feat_loss_kernel<<<sms * 8, 256, 0, st>>>(a);
   return check_cuda(cudaGetLastError(), "feat_loss launch");
 }
 
 int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_loss, void* stream) {
   if (!partials || !out_loss || n_images <= 0) return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_finalize: bad argument");
-  feat_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_images, out_loss);
+  note_launch(); feat_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_images, out_loss);
   return check_cuda(cudaGetLastError(), "feat_finalize launch");
 }
 
@@ -433,15 +433,15 @@ int mvsdf_rgb_l1_partials(const float* rgb_values, const float* rgb_gt, const ui
   if (rc) return rc;
   const int sms = sm_count();
   if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
-  set_double_kernel<<<1, 32, 0, st>>>(partials + 1, (double)n_rays);
+  note_launch(); set_double_kernel<<<1, 32, 0, st>>>(partials + 1, (double)n_rays);
   const int grid = (int)std::min<int64_t>((n_rays + kBlk - 1) / kBlk, (int64_t)sms * 8);
-  rgb_l1_kernel<<<grid, kBlk, 0, st>>>(rgb_values, rgb_gt, mask, n_rays, partials);
+  note_launch(); rgb_l1_kernel<<<grid, kBlk, 0, st>>>(rgb_values, rgb_gt, mask, n_rays, partials);
   return check_cuda(cudaGetLastError(), "rgb_l1 launch");
 }
 
 int mvsdf_rgb_l1_finalize(const double* partials, float* out_loss, void* stream) {
   if (!partials || !out_loss) return fail(MVSDF_ERR_INVALID, "mvsdf_rgb_l1_finalize: bad argument");
-  rgb_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, out_loss);
+  note_launch(); rgb_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, out_loss);
   return check_cuda(cudaGetLastError(), "rgb_finalize launch");
 }
 

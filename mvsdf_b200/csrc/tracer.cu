@@ -494,57 +494,57 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     return mlp_sdf(net, packed, c.req_pts, 0, c.counters + counter, MVSDF_HEAD_SDF_ONLY, c.req_val, nullptr, nullptr,
                    false, st);
   };
-  ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr);
+  note_launch(); ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr);
   if ((rc = eval(ctr++))) return rc;
   for (int it = 0; it < prm->sphere_tracing_iters; ++it) {
-    trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr);
+    note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr);
     if ((rc = eval(ctr++))) return rc;
     for (int k = 0; k < prm->line_step_iters; ++k) {
-      trace_backoff_kernel<<<grid_r, kBlock, 0, st>>>(c, k, ctr);
+      note_launch(); trace_backoff_kernel<<<grid_r, kBlock, 0, st>>>(c, k, ctr);
       if ((rc = eval(ctr++))) return rc;
     }
   }
-  trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr);
+  note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr);
   const int list_ctr = ctr++;
-  trace_finish_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr);
+  note_launch(); trace_finish_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr);
   // sampler in batches of batch_rays rays (worst case: every ray unconverged)
   const int n_batches = (int)((R + w.batch_rays - 1) / w.batch_rays);
   for (int b = 0; b < n_batches; ++b) {
     const int begin = b * w.batch_rays;
     const long long items = (long long)w.batch_rays * kSteps;
-    sampler_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, linspace100, list_ctr, begin,
+    note_launch(); sampler_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, linspace100, list_ctr, begin,
                                                                                 w.batch_rays, ctr);
     if ((rc = eval(ctr))) return rc;
-    sampler_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, linspace100, object_mask, training,
+    note_launch(); sampler_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, linspace100, object_mask, training,
                                                                                    list_ctr, begin, w.batch_rays);
     ctr++;
     if (ctr >= kNumCounters - 24) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many sampler batches");
   }
   for (int i = 0; i <= prm->n_secant_steps; ++i) {
     const int push = i < prm->n_secant_steps;
-    secant_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr, i > 0, push, ctr);
+    note_launch(); secant_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr, i > 0, push, ctr);
     if (push) {
       if ((rc = eval(ctr++))) return rc;
     }
   }
   if (training) {
     const int ml_ctr = ctr++;
-    minsdf_prepare_kernel<<<grid_r, kBlock, 0, st>>>(c, object_mask, ml_ctr);
+    note_launch(); minsdf_prepare_kernel<<<grid_r, kBlock, 0, st>>>(c, object_mask, ml_ctr);
     if (!prm->skip_min_sdf) {
       for (int b = 0; b < n_batches; ++b) {
         const int begin = b * w.batch_rays;
         const long long items = (long long)w.batch_rays * kSteps;
-        minsdf_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
+        note_launch(); minsdf_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
                                                                                    w.batch_rays, ctr);
         if ((rc = eval(ctr))) return rc;
-        minsdf_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
+        note_launch(); minsdf_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
                                                                                       w.batch_rays);
         ctr++;
         if (ctr >= kNumCounters - 2) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many min-sdf batches");
       }
     }
   }
-  trace_output_kernel<<<grid_r, kBlock, 0, st>>>(c, out_dists, out_net_mask, out_points);
+  note_launch(); trace_output_kernel<<<grid_r, kBlock, 0, st>>>(c, out_dists, out_net_mask, out_points);
   if (out_counters)
     rc = check_cuda(cudaMemcpyAsync(out_counters, c.counters, kNumCounters * 4, cudaMemcpyDeviceToDevice, st),
                     "copy counters");
