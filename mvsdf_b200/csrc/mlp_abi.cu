@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -163,26 +164,71 @@ static int fill_args(const NetPlan& p, const void* packed, int head, MlpArgs& a)
   return MVSDF_OK;
 }
 
-template <int KIND, int MODE>
-static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_dev, cudaStream_t st) {
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int KIND, int MODE, int CL>
+static int launch_mlp_cl(const NetPlan& p, MlpArgs& a, long long tiles, bool device_count, cudaStream_t st) {
   const int sms = sm_count();
-  if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
-  a.n = n;
-  a.n_ptr = n_dev;
-  const int per_tile = MODE == 0 ? kTileN : kTileN / 4;
-  long long tiles = (n + per_tile - 1) / per_tile;
-  if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
-  const int grid = n_dev ? sms : (int)std::min<long long>(tiles, sms);
   const size_t smem = mlp_smem_bytes(p.k_cores_max);
-  auto kern = mlp_tile_kernel<KIND, MODE>;
+  auto kern = mlp_tile_kernel<KIND, MODE, CL>;
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(mlp_tile_kernel)");
   if (rc) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kMlpThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  // persistent grid: as many co-resident clusters as the device can hold (cached per instantiation)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    if (CL == 1) {
+      max_clusters = sms;
+    } else {
+      cfg.gridDim = dim3((sms / CL) * CL);
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters <= 0) {
+        cudaGetLastError();
+        max_clusters = std::max(1, sms / CL - 2);
+      }
+      max_clusters = std::min(max_clusters, sms / CL);
+    }
+  }
+  const long long groups = (tiles + CL - 1) / CL;
+  const int n_clusters = device_count ? max_clusters : (int)std::min<long long>(groups, max_clusters);
+  cfg.gridDim = dim3(n_clusters * CL);
   const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : 0));
   ProfEvent* pe = prof_begin(kind, st);
-  note_launch(); kern<<<grid, kMlpThreads, smem, st>>>(a);
+  note_launch();
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "launch mlp_tile_kernel");
   prof_end(pe, st);
-  return check_cuda(cudaGetLastError(), "launch mlp_tile_kernel");
+  return rc;
+}
+
+template <int KIND, int MODE>
+static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_dev, cudaStream_t st) {
+  if (sm_count() <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
+  a.n = n;
+  a.n_ptr = n_dev;
+  static const int cl = env_int("MVSDF_CLUSTER", 4);
+  static const int dbg = env_int("MVSDF_DEBUG_FLAGS", 0);
+  a.debug = dbg;
+  const int per_tile = MODE == 0 ? kTileN : kTileN / 4;
+  const long long tiles = (n + per_tile - 1) / per_tile;
+  if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
+  // small host-known batches cannot fill clusters: fall back to single-CTA scheduling (same kernel, CL = 1)
+  const bool small = n_dev == nullptr && tiles < 2 * sm_count();
+  if (cl >= 4 && !small) return launch_mlp_cl<KIND, MODE, 4>(p, a, tiles, n_dev != nullptr, st);
+  if (cl >= 2 && !small) return launch_mlp_cl<KIND, MODE, 2>(p, a, tiles, n_dev != nullptr, st);
+  return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, n_dev != nullptr, st);
 }
 
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,

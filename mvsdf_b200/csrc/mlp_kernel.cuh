@@ -45,6 +45,7 @@ struct MlpArgs {
   int k_cores_max;
   int head;                  // HeadKind
   int feat_size;
+  int debug;                 // bit0 skip weight copies, bit1 skip UMMAs, bit2 skip epilogue math (bottleneck isolation only)
   int feat_stride;           // row stride (floats) of `feats`; lets the render pass read full[:, 2:] in place
   long long n;               // number of points (ignored when n_ptr != nullptr)
   const int* n_ptr;          // optional device-side count
@@ -86,7 +87,7 @@ __device__ __forceinline__ float softplus100(float z, float& sig) {
   return t > 20.0f ? z : y;
 }
 
-template <int KIND, int MODE>
+template <int KIND, int MODE, int CL>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -110,11 +111,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
   const long long n_pts = a.n_ptr ? (long long)(*a.n_ptr) : a.n;
   constexpr int kPtsPerTile = (MODE == 0) ? kTileN : kTileN / 4;
   const long long n_tiles = (n_pts + kPtsPerTile - 1) / kPtsPerTile;
+  // A cluster of CL CTAs walks the tile list together (CTA rank r takes tile g*CL + r) so that all of them
+  // consume the same weight stream: every stage is fetched from L2 once per cluster and multicast.
+  const uint32_t crank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+  const long long n_groups = (n_tiles + CL - 1) / CL;
+  const long long group0 = blockIdx.x / CL;
+  const long long group_stride = gridDim.x / CL;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_empty + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, CL);
     }
     ptx::mbar_init(bar_acc, 1);
     ptx::mbar_init(bar_act, kEpiWarps);
@@ -126,23 +134,34 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();      // barrier inits visible cluster-wide before any remote arrive / multicast
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - s_stage));
 
   if (warp == kEpiWarps) {
     // ------------------------------------------------------------------ weight producer
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    constexpr uint32_t kSlice = kStageBytes / CL;
+    for (long long g = group0; g < n_groups; g += group_stride) {
       for (int l = 0; l < a.n_run; ++l) {
         const LayerPlan& lp = a.L[l];
         const uint8_t* src = a.packed + lp.w_off;
         const int n_stage = lp.m_tiles * lp.k_chunks;
         for (int i = 0; i < n_stage; ++i, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);     // every CTA of the cluster has drained this stage
           if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
-            ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)i * kStageBytes, kStageBytes, bar_full + 8 * s);
+            if (a.debug & 1) {
+              ptx::mbar_arrive(bar_full + 8 * s);
+            } else {
+              ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
+              if (CL == 1)
+                ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)i * kStageBytes, kStageBytes, bar_full + 8 * s);
+              else
+                ptx::bulk_g2s_multicast(s_stage + s * kStageBytes + crank * kSlice,
+                                        src + (size_t)i * kStageBytes + crank * kSlice, kSlice, bar_full + 8 * s,
+                                        kClusterMask);
+            }
           }
           __syncwarp();
         }
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
     // ------------------------------------------------------------------ UMMA issuer
     constexpr uint32_t idesc = ptx::idesc_f16_f32(kTileM, kTileN);
     uint32_t it = 0, act_ctr = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long g = group0; g < n_groups; g += group_stride) {
       for (int l = 0; l < a.n_run; ++l) {
         const LayerPlan& lp = a.L[l];
         ptx::mbar_wait(bar_act, act_ctr & 1);
@@ -176,11 +195,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
                 const uint32_t boff = (uint32_t)((kc * (kChunkK / 8) + ks * 2) * kBCoreStride);
                 const uint64_t db_hi = ptx::smem_desc(b_hi + boff, kBCoreStride, 128);
                 const uint64_t db_lo = ptx::smem_desc(b_lo + boff, kBCoreStride, 128);
-                ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
-                ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-                ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                if (!(a.debug & 2)) {
+                  ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
+                  ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+                  ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                }
               }
-              ptx::umma_commit(bar_empty + 8 * s);   // frees the stage once these UMMAs have read it
+              // frees the stage (in every CTA of the cluster) once these UMMAs have read it
+              if (CL == 1) ptx::umma_commit(bar_empty + 8 * s);
+              else ptx::umma_commit_multicast(bar_empty + 8 * s, kClusterMask);
             }
             __syncwarp();
           }
@@ -198,7 +221,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
     constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
     uint32_t acc_ctr = 0;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long g = group0; g < n_groups; g += group_stride) {
+      const long long tile = g * CL + crank;            // tiles past the end run on zero points, outputs are guarded
       const long long p0 = tile * kPtsPerTile;
 
       // ---------------- prologue: build the first layer's B operand
@@ -317,7 +341,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
               for (int j = 0; j < 32; ++j) {
                 const float z = fmaf(__uint_as_float(v[j]), kInvScale, bias);
                 float y, sg;
-                if (lp.act == ACT_SOFTPLUS100) y = softplus100(z, sg);
+                if (a.debug & 4) y = z;
+                else if (lp.act == ACT_SOFTPLUS100) y = softplus100(z, sg);
                 else if (lp.act == ACT_RELU) y = fmaxf(z, 0.0f);
                 else y = z;
                 const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
@@ -386,6 +411,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync();      // no CTA may exit while peers can still multicast into it
   if (warp == kEpiWarps + 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
