@@ -218,7 +218,7 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   if (sm_count() <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
   a.n = n;
   a.n_ptr = n_dev;
-  static const int cl = env_int("MVSDF_CLUSTER", 4);
+  static const int cl = env_int("MVSDF_CLUSTER", 1);   // multicast clusters measured no faster (profiles/r01): L2 is not the bound
   static const int dbg = env_int("MVSDF_DEBUG_FLAGS", 0);
   a.debug = dbg;
   const int per_tile = MODE == 0 ? kTileN : kTileN / 4;

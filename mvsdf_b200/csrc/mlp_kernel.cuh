@@ -76,15 +76,30 @@ __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, 
   ptx::st_shared_u16(lo_addr, __half_as_ushort(l));
 }
 
-// softplus(beta=100, threshold=20) as torch computes it: z if 100 z > 20 else log1p(exp(100 z))/100
-// (nn.Softplus(beta=100), implicit_differentiable_renderer.py:75). Also returns d/dz = sigmoid(100 z).
-__device__ __forceinline__ float softplus100(float z, float& sig) {
-  const float t = z * 100.0f;
-  const float e = ptx::ex2_approx(fminf(t, 20.0f) * 1.4426950408889634f);
+__device__ __forceinline__ float select_gt(float a, float thr, float if_true, float if_false) {
+  // branch-free select; inline PTX so that ptxas cannot turn it into a divergent branch around the MUFU ops
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\tselp.f32 %0, %3, %4, p;\n\t}" : "=f"(r) : "f"(a), "f"(thr), "f"(if_true), "f"(if_false));
+  return r;
+}
+
+// kActScale * softplus(z; beta=100, threshold=20), as torch computes it: z if 100 z > 20 else log1p(exp(100 z))/100
+// (nn.Softplus(beta=100), implicit_differentiable_renderer.py:75).  Straight-line code: ex2/lg2 on the SFU,
+// overflow to +inf above the threshold is discarded by the select.
+__device__ __forceinline__ float softplus100_scaled(float z) {
+  const float tl = z * (100.0f * 1.4426950408889634f);                 // 100 z log2(e)
+  const float e = ptx::ex2_approx(tl);
+  const float y = ptx::lg2_approx(1.0f + e) * (kActScale * 0.6931471805599453f * 0.01f);
+  return select_gt(tl, 20.0f * 1.4426950408889634f, z * kActScale, y);
+}
+// same, also returning d softplus / dz = sigmoid(100 z)
+__device__ __forceinline__ float softplus100_scaled_grad(float z, float& sig) {
+  const float tl = z * (100.0f * 1.4426950408889634f);
+  const float e = ptx::ex2_approx(tl);
   const float ope = 1.0f + e;
-  const float y = ptx::lg2_approx(ope) * (0.6931471805599453f * 0.01f);
-  sig = t > 20.0f ? 1.0f : e * ptx::rcp_approx(ope);
-  return t > 20.0f ? z : y;
+  const float y = ptx::lg2_approx(ope) * (kActScale * 0.6931471805599453f * 0.01f);
+  sig = select_gt(tl, 20.0f * 1.4426950408889634f, 1.0f, e * ptx::rcp_approx(ope));
+  return select_gt(tl, 20.0f * 1.4426950408889634f, z * kActScale, y);
 }
 
 template <int KIND, int MODE, int CL>
@@ -317,86 +332,96 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
         ptx::mbar_wait(bar_acc, acc_ctr & 1);
         ++acc_ctr;
         ptx::tc_fence_after();
-        for (int m = 0; m < lp.m_tiles; ++m) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * kTileN + h * 32), v);
-          ptx::tmem_ld_wait();
-          const int f = m * kTileM + row;
-          const float bias = __ldg(a.bias + lp.bias_off + f);
-          if (!last) {
-            const uint32_t o0 = xoff(h * 32, f);
-            if (l == a.skip_layer - 1 && f >= a.skip_rows_begin) {
-              // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
-              const int k = f - a.skip_rows_begin;
-              const uint32_t s0 = xoff(h * 32, k);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32);
+        // per 128-row tile: TMEM -> registers -> activation -> fp16 hi/lo -> next layer's B operand (or global)
+        auto process_tile = [&](const int m, const uint32_t(&v)[32]) {
+            const int f = m * kTileM + row;
+            const float bias = __ldg(a.bias + lp.bias_off + f);
+            if (!last) {
+              const uint32_t o0 = xoff(h * 32, f);
+              if (KIND == NET_SDF && l == a.skip_layer - 1 && f >= a.skip_rows_begin) {
+                // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
+                const int k = f - a.skip_rows_begin;
+                const uint32_t s0 = xoff(h * 32, k);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
-                const bool real = k < a.pe_dim;
-                ptx::st_shared_u16(s_xhi + o0 + d, real ? ptx::ld_shared_u16(s_pehi + s0 + d) : (uint16_t)0);
-                ptx::st_shared_u16(s_xlo + o0 + d, real ? ptx::ld_shared_u16(s_pelo + s0 + d) : (uint16_t)0);
-              }
-            } else if (MODE == 0) {
+                for (int j = 0; j < 32; ++j) {
+                  const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                  const bool real = k < a.pe_dim;
+                  ptx::st_shared_u16(s_xhi + o0 + d, real ? ptx::ld_shared_u16(s_pehi + s0 + d) : (uint16_t)0);
+                  ptx::st_shared_u16(s_xlo + o0 + d, real ? ptx::ld_shared_u16(s_pelo + s0 + d) : (uint16_t)0);
+                }
+              } else if (MODE == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float z = fmaf(__uint_as_float(v[j]), kInvScale, bias);
-                float y, sg;
-                if (a.debug & 4) y = z;
-                else if (lp.act == ACT_SOFTPLUS100) y = softplus100(z, sg);
-                else if (lp.act == ACT_RELU) y = fmaxf(z, 0.0f);
-                else y = z;
-                const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
-                store_split(s_xhi + o0 + d, s_xlo + o0 + d, y * kActScale);
-              }
-            } else {
+                for (int j = 0; j < 32; ++j) {
+                  const float z = fmaf(__uint_as_float(v[j]), kInvScale, bias);
+                  const float ys = (KIND == NET_SDF) ? softplus100_scaled(z) : fmaxf(z, 0.0f) * kActScale;
+                  const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                  store_split(s_xhi + o0 + d, s_xlo + o0 + d, ys);
+                }
+              } else {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float z = fmaf(__uint_as_float(v[4 * g]), kInvScale, bias);
-                float sg;
-                const float y = softplus100(z, sg);
-                const uint32_t d0 = (uint32_t)(((4 * g) >> 3) * 128 + ((4 * g) & 7) * 16);
-                store_split(s_xhi + o0 + d0, s_xlo + o0 + d0, y * kActScale);
-                const float ts = sg * (kInvScale * kActScale);
+                for (int g = 0; g < 8; ++g) {
+                  const float z = fmaf(__uint_as_float(v[4 * g]), kInvScale, bias);
+                  float sg;
+                  const float ys = softplus100_scaled_grad(z, sg);
+                  const uint32_t d0 = (uint32_t)(((4 * g) >> 3) * 128 + ((4 * g) & 7) * 16);
+                  store_split(s_xhi + o0 + d0, s_xlo + o0 + d0, ys);
+                  const float ts = sg * (kInvScale * kActScale);
 #pragma unroll
-                for (int jj = 1; jj < 4; ++jj) {
-                  const uint32_t d = d0 + jj * 16;
-                  store_split(s_xhi + o0 + d, s_xlo + o0 + d, __uint_as_float(v[4 * g + jj]) * ts);
+                  for (int jj = 1; jj < 4; ++jj) {
+                    const uint32_t d = d0 + jj * 16;
+                    store_split(s_xhi + o0 + d, s_xlo + o0 + d, __uint_as_float(v[4 * g + jj]) * ts);
+                  }
                 }
               }
-            }
-          } else {
-            // ---------------- head: write results to global memory
+            } else {
+              // ---------------- head: write results to global memory
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = h * 32 + j;
-              const float acc = __uint_as_float(v[j]) * kInvScale;
-              if (KIND == NET_RENDER) {
-                const long long gp = p0 + col;
-                if (row < 3 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
-              } else {
-                const long long gp = (MODE == 0) ? p0 + col : p0 + (col >> 2);
-                const int jj = (MODE == 0) ? 0 : (col & 3);
-                if (gp < n_pts) {
-                  if (a.head == HEAD_SDF_ONLY) {
-                    if (row == 0) {
-                      if (jj == 0) a.out_sdf[gp] = acc + bias;
-                      else a.out_grad[gp * 3 + jj - 1] = acc;
-                    }
-                  } else {
-                    const int F = a.feat_size;
-                    if (jj == 0) {
-                      if (f < F) a.out_full[gp * (F + 2) + 2 + f] = acc + bias;
-                      else if (f < F + 2) {
-                        a.out_full[gp * (F + 2) + (f - F)] = acc + bias;
-                        if (f == F && a.out_sdf) a.out_sdf[gp] = acc + bias;
+              for (int j = 0; j < 32; ++j) {
+                const int col = h * 32 + j;
+                const float acc = __uint_as_float(v[j]) * kInvScale;
+                if (KIND == NET_RENDER) {
+                  const long long gp = p0 + col;
+                  if (row < 3 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
+                } else {
+                  const long long gp = (MODE == 0) ? p0 + col : p0 + (col >> 2);
+                  const int jj = (MODE == 0) ? 0 : (col & 3);
+                  if (gp < n_pts) {
+                    if (a.head == HEAD_SDF_ONLY) {
+                      if (row == 0) {
+                        if (jj == 0) a.out_sdf[gp] = acc + bias;
+                        else a.out_grad[gp * 3 + jj - 1] = acc;
                       }
-                    } else if (f == F) {
-                      a.out_grad[gp * 3 + jj - 1] = acc;
+                    } else {
+                      const int F = a.feat_size;
+                      if (jj == 0) {
+                        if (f < F) a.out_full[gp * (F + 2) + 2 + f] = acc + bias;
+                        else if (f < F + 2) {
+                          a.out_full[gp * (F + 2) + (f - F)] = acc + bias;
+                          if (f == F && a.out_sdf) a.out_sdf[gp] = acc + bias;
+                        }
+                      } else if (f == F) {
+                        a.out_grad[gp * 3 + jj - 1] = acc;
+                      }
                     }
                   }
                 }
               }
             }
+        };
+        // software pipeline over the tiles: the TMEM load of tile m+1 is in flight while tile m is processed
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32(t_row, v0);
+        ptx::tmem_ld_wait();
+#pragma unroll 1
+        for (int m = 0; m < lp.m_tiles; m += 2) {
+          if (m + 1 < lp.m_tiles) ptx::tmem_ld_32x32(t_row + (uint32_t)((m + 1) * kTileN), v1);
+          process_tile(m, v0);
+          ptx::tmem_ld_wait();
+          if (m + 1 < lp.m_tiles) {
+            if (m + 2 < lp.m_tiles) ptx::tmem_ld_32x32(t_row + (uint32_t)((m + 2) * kTileN), v0);
+            process_tile(m + 1, v1);
+            ptx::tmem_ld_wait();
           }
         }
         if (!last) {

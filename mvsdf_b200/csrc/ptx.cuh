@@ -159,7 +159,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v));
 }
 __device__ __forceinline__ uint16_t ld_shared_u16(uint32_t addr) {
   uint16_t v;
