@@ -10,9 +10,12 @@
 //     padded K-core stride so the epilogue's 2-byte stores are bank-conflict free);
 //   * 3 UMMAs per K step (hi*hi + lo*hi + hi*lo) give ~22-bit operands with fp32 accumulation in
 //     TMEM -- the reference's fp32 SGEMM accuracy (SURVEY.md fact 0.9 rules out plain TF32/BF16);
-//   * epilogue (warps 0-7): TMEM -> registers -> bias + softplus(beta=100)/ReLU -> fp16 split ->
-//     shared memory, which is the next layer's B operand; forward-mode tangents ride along as
-//     extra columns (value+gradient mode) and are scaled by sigmoid(100 z).
+//   * epilogue (warps 0-15): as soon as the UMMAs of one 128-row output tile have committed (one mbarrier
+//     per tile) its accumulators go TMEM -> registers -> bias + softplus(beta=100)/ReLU -> fp16 hi/lo and
+//     are parked in registers while the tensor core works on the next tiles; once the layer's last UMMA
+//     has retired the parked values overwrite the activation buffer in place (it is the next layer's B
+//     operand).  Forward-mode tangents ride along as extra columns (value+gradient mode) and are scaled
+//     by sigmoid(100 z).
 //
 // Replaces, per call, the reference's embedder + 9 SGEMMs + softplus kernels
 // (model/embedder.py:35, model/implicit_differentiable_renderer.py:77-94) and, in value+gradient mode,
@@ -28,12 +31,13 @@
 
 namespace mvsdf {
 
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;              // 4 TMEM lane quarters x 4 column groups of 16
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMlpThreads = kEpiThreads + 64;   // + producer warp + MMA warp
 constexpr int kPeCores = 8;                     // PE tile: K padded to 64
 constexpr int kPeTileBytes = kPeCores * kBCoreStride;
-constexpr int kScratchStride = 40;              // floats per point in the prologue scratch
+constexpr int kScratchStride = 40;
+constexpr int kMaxTiles = 4;                   // 128-row output tiles per layer (width <= 512)              // floats per point in the prologue scratch
 
 struct MlpArgs {
   const uint8_t* packed;
@@ -76,6 +80,15 @@ __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, 
   ptx::st_shared_u16(lo_addr, __half_as_ushort(l));
 }
 
+// two activated values -> packed fp16 (hi, hi) and (lo, lo) registers: x = hi + lo to ~22 bits
+__device__ __forceinline__ void pack_split(float y0, float y1, uint32_t& hi2, uint32_t& lo2) {
+  const __half2 h = __floats2half2_rn(y0, y1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ float select_gt(float a, float thr, float if_true, float if_false) {
   // branch-free select; inline PTX so that ptxas cannot turn it into a divergent branch around the MUFU ops
   float r;
@@ -116,8 +129,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
   const uint32_t s_bar = s_pelo + kPeTileBytes;          // 16-byte aligned by construction
   const uint32_t bar_full = s_bar;                       // kStages x 8 B
   const uint32_t bar_empty = s_bar + 8 * kStages;
-  const uint32_t bar_acc = s_bar + 16 * kStages;         // MMA -> epilogue: layer accumulators complete
-  const uint32_t bar_act = bar_acc + 8;                  // epilogue -> MMA: next B operand ready, TMEM drained
+  const uint32_t bar_acc = s_bar + 16 * kStages;         // kMaxTiles x 8 B, MMA -> epilogue: tile m accumulators complete
+  const uint32_t bar_act = bar_acc + 8 * kMaxTiles;      // epilogue -> MMA: next B operand ready, TMEM drained
   const uint32_t s_tmem = bar_act + 8;
   uint8_t* const g_scratch = (KIND == NET_SDF) ? (smem + kStages * kStageBytes)
                                                : (smem + kStages * kStageBytes + 2 * xbytes);
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
       ptx::mbar_init(bar_full + 8 * s, 1);
       ptx::mbar_init(bar_empty + 8 * s, CL);
     }
-    ptx::mbar_init(bar_acc, 1);
+    for (int m = 0; m < kMaxTiles; ++m) ptx::mbar_init(bar_acc + 8 * m, 1);
     ptx::mbar_init(bar_act, kEpiWarps);
     ptx::fence_mbar_init();
   }
@@ -222,19 +235,20 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
             }
             __syncwarp();
           }
+          // this tile's accumulators are final: the epilogue may start on it while the next tile is computed
+          if (lane == 0) ptx::umma_commit(bar_acc + 8 * m);
+          __syncwarp();
         }
-        if (lane == 0) ptx::umma_commit(bar_acc);
-        __syncwarp();
       }
     }
   } else {
     // ------------------------------------------------------------------ prologue + epilogue warps
     const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int h = warp >> 2;             // column half
+    const int cg = warp >> 2;            // column group: columns 16*cg .. 16*cg+15
     const int row = q * 32 + lane;       // row inside a 128-row output tile
-    const int t = threadIdx.x;           // 0..255
+    const int t = threadIdx.x;           // 0..kEpiThreads-1
     constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
-    uint32_t acc_ctr = 0;
+    uint32_t acc_ctr[kMaxTiles] = {0, 0, 0, 0};
 
     for (long long g = group0; g < n_groups; g += group_stride) {
       const long long tile = g * CL + crank;            // tiles past the end run on zero points, outputs are guarded
@@ -329,56 +343,48 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
       for (int l = 0; l < a.n_run; ++l) {
         const LayerPlan& lp = a.L[l];
         const bool last = (l == a.n_run - 1);
-        ptx::mbar_wait(bar_acc, acc_ctr & 1);
-        ++acc_ctr;
-        ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32);
-        // per 128-row tile: TMEM -> registers -> activation -> fp16 hi/lo -> next layer's B operand (or global)
-        auto process_tile = [&](const int m, const uint32_t(&v)[32]) {
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16);
+        const bool skip_src = KIND == NET_SDF && l == a.skip_layer - 1;
+        // activated outputs of the layer, fp16 hi/lo, two columns per register; parked until the layer's UMMAs retire
+        uint32_t phi[kMaxTiles][8], plo[kMaxTiles][8];
+#pragma unroll
+        for (int m = 0; m < kMaxTiles; ++m) {
+          if (m < lp.m_tiles) {
+            ptx::mbar_wait(bar_acc + 8 * m, acc_ctr[m] & 1);
+            ++acc_ctr[m];
+            ptx::tc_fence_after();
+            uint32_t v[16];
+            ptx::tmem_ld_32x16(t_row + (uint32_t)(m * kTileN), v);
+            ptx::tmem_ld_wait();
             const int f = m * kTileM + row;
             const float bias = __ldg(a.bias + lp.bias_off + f);
             if (!last) {
-              const uint32_t o0 = xoff(h * 32, f);
-              if (KIND == NET_SDF && l == a.skip_layer - 1 && f >= a.skip_rows_begin) {
-                // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
-                const int k = f - a.skip_rows_begin;
-                const uint32_t s0 = xoff(h * 32, k);
+              if (MODE == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
-                  const bool real = k < a.pe_dim;
-                  ptx::st_shared_u16(s_xhi + o0 + d, real ? ptx::ld_shared_u16(s_pehi + s0 + d) : (uint16_t)0);
-                  ptx::st_shared_u16(s_xlo + o0 + d, real ? ptx::ld_shared_u16(s_pelo + s0 + d) : (uint16_t)0);
-                }
-              } else if (MODE == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float z = fmaf(__uint_as_float(v[j]), kInvScale, bias);
-                  const float ys = (KIND == NET_SDF) ? softplus100_scaled(z) : fmaxf(z, 0.0f) * kActScale;
-                  const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
-                  store_split(s_xhi + o0 + d, s_xlo + o0 + d, ys);
+                for (int i = 0; i < 8; ++i) {
+                  const float z0 = fmaf(__uint_as_float(v[2 * i]), kInvScale, bias);
+                  const float z1 = fmaf(__uint_as_float(v[2 * i + 1]), kInvScale, bias);
+                  const float y0 = (KIND == NET_SDF) ? softplus100_scaled(z0) : fmaxf(z0, 0.0f) * kActScale;
+                  const float y1 = (KIND == NET_SDF) ? softplus100_scaled(z1) : fmaxf(z1, 0.0f) * kActScale;
+                  pack_split(y0, y1, phi[m][i], plo[m][i]);
                 }
               } else {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float z = fmaf(__uint_as_float(v[4 * g]), kInvScale, bias);
+                for (int gq = 0; gq < 4; ++gq) {
+                  const float z = fmaf(__uint_as_float(v[4 * gq]), kInvScale, bias);
                   float sg;
-                  const float ys = softplus100_scaled_grad(z, sg);
-                  const uint32_t d0 = (uint32_t)(((4 * g) >> 3) * 128 + ((4 * g) & 7) * 16);
-                  store_split(s_xhi + o0 + d0, s_xlo + o0 + d0, ys);
+                  const float y = softplus100_scaled_grad(z, sg);
                   const float ts = sg * (kInvScale * kActScale);
-#pragma unroll
-                  for (int jj = 1; jj < 4; ++jj) {
-                    const uint32_t d = d0 + jj * 16;
-                    store_split(s_xhi + o0 + d, s_xlo + o0 + d, __uint_as_float(v[4 * g + jj]) * ts);
-                  }
+                  pack_split(y, __uint_as_float(v[4 * gq + 1]) * ts, phi[m][2 * gq], plo[m][2 * gq]);
+                  pack_split(__uint_as_float(v[4 * gq + 2]) * ts, __uint_as_float(v[4 * gq + 3]) * ts, phi[m][2 * gq + 1],
+                             plo[m][2 * gq + 1]);
                 }
               }
             } else {
               // ---------------- head: write results to global memory
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = h * 32 + j;
+              for (int j = 0; j < 16; ++j) {
+                const int col = cg * 16 + j;
                 const float acc = __uint_as_float(v[j]) * kInvScale;
                 if (KIND == NET_RENDER) {
                   const long long gp = p0 + col;
@@ -408,23 +414,38 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
                 }
               }
             }
-        };
-        // software pipeline over the tiles: the TMEM load of tile m+1 is in flight while tile m is processed
-        uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32(t_row, v0);
-        ptx::tmem_ld_wait();
-#pragma unroll 1
-        for (int m = 0; m < lp.m_tiles; m += 2) {
-          if (m + 1 < lp.m_tiles) ptx::tmem_ld_32x32(t_row + (uint32_t)((m + 1) * kTileN), v1);
-          process_tile(m, v0);
-          ptx::tmem_ld_wait();
-          if (m + 1 < lp.m_tiles) {
-            if (m + 2 < lp.m_tiles) ptx::tmem_ld_32x32(t_row + (uint32_t)((m + 2) * kTileN), v0);
-            process_tile(m + 1, v1);
-            ptx::tmem_ld_wait();
           }
         }
         if (!last) {
+          // every UMMA of this layer has retired (commits complete in order): overwrite the activation buffer in place
+#pragma unroll
+          for (int m = 0; m < kMaxTiles; ++m) {
+            if (m < lp.m_tiles) {
+              const int f = m * kTileM + row;
+              const uint32_t o0 = xoff(cg * 16, f);
+              if (skip_src && f >= a.skip_rows_begin) {
+                // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
+                const int k = f - a.skip_rows_begin;
+                const uint32_t s0 = xoff(cg * 16, k);
+                const bool real = k < a.pe_dim;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
+                  ptx::st_shared_u16(s_xhi + o0 + d, real ? ptx::ld_shared_u16(s_pehi + s0 + d) : (uint16_t)0);
+                  ptx::st_shared_u16(s_xlo + o0 + d, real ? ptx::ld_shared_u16(s_pelo + s0 + d) : (uint16_t)0);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const uint32_t d = (uint32_t)(((2 * i) >> 3) * 128 + ((2 * i) & 7) * 16);
+                  ptx::st_shared_u16(s_xhi + o0 + d, (uint16_t)(phi[m][i] & 0xffffu));
+                  ptx::st_shared_u16(s_xhi + o0 + d + 16, (uint16_t)(phi[m][i] >> 16));
+                  ptx::st_shared_u16(s_xlo + o0 + d, (uint16_t)(plo[m][i] & 0xffffu));
+                  ptx::st_shared_u16(s_xlo + o0 + d + 16, (uint16_t)(plo[m][i] >> 16));
+                }
+              }
+            }
+          }
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           __syncwarp();
