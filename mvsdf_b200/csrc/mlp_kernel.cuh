@@ -65,7 +65,7 @@ struct MlpArgs {
 };
 
 __host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
-  return (size_t)kStages * kStageBytes + 2 * (size_t)k_cores_max * kBCoreStride + 2 * kPeTileBytes + 128;
+  return (size_t)kStages * kStageBytes + (size_t)k_cores_max * kBCoreStride + kPeTileBytes + 128;
 }
 
 // byte offset of (column n, feature k) inside an activation operand buffer
@@ -122,21 +122,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
   const int lane = threadIdx.x & 31;
   const uint32_t xbytes = (uint32_t)a.k_cores_max * kBCoreStride;
   const uint32_t s_stage = ptx::smem_u32(smem);
-  const uint32_t s_xhi = s_stage + kStages * kStageBytes;
-  const uint32_t s_xlo = s_xhi + xbytes;
-  const uint32_t s_pehi = s_xlo + xbytes;
-  const uint32_t s_pelo = s_pehi + kPeTileBytes;
-  const uint32_t s_bar = s_pelo + kPeTileBytes;          // 16-byte aligned by construction
+  const uint32_t s_xhi = s_stage + kStages * kStageBytes;   // activation operand [hi | lo] interleaved per K core
+  const uint32_t s_xlo = s_xhi + kBLoOffset;
+  const uint32_t s_pehi = s_xhi + xbytes;                    // positional-encoding operand, same structure
+  const uint32_t s_pelo = s_pehi + kBLoOffset;
+  const uint32_t s_bar = s_pehi + kPeTileBytes;              // 16-byte aligned by construction
   const uint32_t bar_full = s_bar;                       // kStages x 8 B
   const uint32_t bar_empty = s_bar + 8 * kStages;
   const uint32_t bar_acc = s_bar + 16 * kStages;         // kMaxTiles x 8 B, MMA -> epilogue: tile m accumulators complete
   const uint32_t bar_act = bar_acc + 8 * kMaxTiles;      // epilogue -> MMA: next B operand ready, TMEM drained
   const uint32_t s_tmem = bar_act + 8;
   uint8_t* const g_scratch = (KIND == NET_SDF) ? (smem + kStages * kStageBytes)
-                                               : (smem + kStages * kStageBytes + 2 * xbytes);
+                                               : (smem + kStages * kStageBytes + xbytes);
   float* const scratch = reinterpret_cast<float*>(g_scratch);
 
-  const long long n_pts = a.n_ptr ? (long long)(*a.n_ptr) : a.n;
+  // (warp-shuffled so that the compiler can treat the trip counts below as warp-uniform)
+  const int n_dev_count = a.n_ptr ? __shfl_sync(0xffffffffu, *a.n_ptr, 0) : 0;
+  const long long n_pts = a.n_ptr ? (long long)n_dev_count : a.n;
   constexpr int kPtsPerTile = (MODE == 0) ? kTileN : kTileN / 4;
   const long long n_tiles = (n_pts + kPtsPerTile - 1) / kPtsPerTile;
   // A cluster of CL CTAs walks the tile list together (CTA rank r takes tile g*CL + r) so that all of them
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
   __syncthreads();
   if (CL > 1) ptx::cluster_sync();      // barrier inits visible cluster-wide before any remote arrive / multicast
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - s_stage));
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - s_stage)), 0);
 
   if (warp == kEpiWarps) {
     // ------------------------------------------------------------------ weight producer
@@ -197,7 +199,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
     }
   } else if (warp == kEpiWarps + 1) {
     // ------------------------------------------------------------------ UMMA issuer
-    constexpr uint32_t idesc = ptx::idesc_f16_f32(kTileM, kTileN);
+    // Per 16-wide K step:  D[:, 0:128] += W_hi * [X_hi ; X_lo]^T   (N = 128: full tensor rate)
+    //                      D[:, 0:64]  += W_lo * X_hi^T            (N = 64)
+    // the epilogue adds the two 64-column halves, giving W_hi X_hi + W_lo X_hi + W_hi X_lo.
+    constexpr uint32_t idesc128 = ptx::idesc_f16_f32(kTileM, 2 * kTileN);
+    constexpr uint32_t idesc64 = ptx::idesc_f16_f32(kTileM, kTileN);
+    const bool leader = ptx::elect_one();
     uint32_t it = 0, act_ctr = 0;
     for (long long g = group0; g < n_groups; g += group_stride) {
       for (int l = 0; l < a.n_run; ++l) {
@@ -205,38 +212,35 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
         ptx::mbar_wait(bar_act, act_ctr & 1);
         ++act_ctr;
         ptx::tc_fence_after();
-        const uint32_t b_hi = lp.b_from_pe ? s_pehi : s_xhi;
-        const uint32_t b_lo = lp.b_from_pe ? s_pelo : s_xlo;
+        const uint32_t b_base = lp.b_from_pe ? s_pehi : s_xhi;
         for (int m = 0; m < lp.m_tiles; ++m) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(m * kTileN);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(m * 2 * kTileN);
           for (int kc = 0; kc < lp.k_chunks; ++kc, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             ptx::mbar_wait(bar_full + 8 * s, ph);
             ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_hi = s_stage + s * kStageBytes;
-              const uint32_t a_lo = a_hi + kTileBytes;
+            const uint32_t a_hi = s_stage + s * kStageBytes;
+            const uint32_t a_lo = a_hi + kTileBytes;
 #pragma unroll
-              for (int ks = 0; ks < kChunkK / 16; ++ks) {
-                const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 256, 128, 512);
-                const uint64_t da_lo = ptx::smem_desc(a_lo + ks * 256, 128, 512);
-                const uint32_t boff = (uint32_t)((kc * (kChunkK / 8) + ks * 2) * kBCoreStride);
-                const uint64_t db_hi = ptx::smem_desc(b_hi + boff, kBCoreStride, 128);
-                const uint64_t db_lo = ptx::smem_desc(b_lo + boff, kBCoreStride, 128);
-                if (!(a.debug & 2)) {
-                  ptx::umma_f16(d_tmem, da_hi, db_hi, idesc, (kc | ks) != 0 ? 1u : 0u);
-                  ptx::umma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-                  ptx::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-                }
+            for (int ks = 0; ks < kChunkK / 16; ++ks) {
+              const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 256, 128, 512);
+              const uint64_t da_lo = ptx::smem_desc(a_lo + ks * 256, 128, 512);
+              const uint64_t db = ptx::smem_desc(b_base + (uint32_t)((kc * (kChunkK / 8) + ks * 2) * kBCoreStride),
+                                                 kBCoreStride, 128);
+              if (leader && !(a.debug & 2)) {
+                ptx::umma_f16(d_tmem, da_hi, db, idesc128, (kc | ks) != 0 ? 1u : 0u);
+                ptx::umma_f16(d_tmem, da_lo, db, idesc64, 1u);
               }
-              // frees the stage (in every CTA of the cluster) once these UMMAs have read it
+            }
+            // frees the stage (in every CTA of the cluster) once these UMMAs have read it
+            if (leader) {
               if (CL == 1) ptx::umma_commit(bar_empty + 8 * s);
               else ptx::umma_commit_multicast(bar_empty + 8 * s, kClusterMask);
             }
             __syncwarp();
           }
           // this tile's accumulators are final: the epilogue may start on it while the next tile is computed
-          if (lane == 0) ptx::umma_commit(bar_acc + 8 * m);
+          if (leader) ptx::umma_commit(bar_acc + 8 * m);
           __syncwarp();
         }
       }
@@ -345,6 +349,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
         const bool last = (l == a.n_run - 1);
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16);
         const bool skip_src = KIND == NET_SDF && l == a.skip_layer - 1;
+        float bias_r[kMaxTiles];          // fetched before the waits so the global-load latency hides behind the UMMAs
+#pragma unroll
+        for (int m = 0; m < kMaxTiles; ++m) bias_r[m] = m < lp.m_tiles ? __ldg(a.bias + lp.bias_off + m * kTileM + row) : 0.f;
         // activated outputs of the layer, fp16 hi/lo, two columns per register; parked until the layer's UMMAs retire
         uint32_t phi[kMaxTiles][8], plo[kMaxTiles][8];
 #pragma unroll
@@ -353,11 +360,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
             ptx::mbar_wait(bar_acc + 8 * m, acc_ctr[m] & 1);
             ++acc_ctr[m];
             ptx::tc_fence_after();
-            uint32_t v[16];
-            ptx::tmem_ld_32x16(t_row + (uint32_t)(m * kTileN), v);
+            uint32_t v[16], v2[16];
+            ptx::tmem_ld_32x16(t_row + (uint32_t)(m * 2 * kTileN), v);
+            ptx::tmem_ld_32x16(t_row + (uint32_t)(m * 2 * kTileN + kTileN), v2);
             ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
             const int f = m * kTileM + row;
-            const float bias = __ldg(a.bias + lp.bias_off + f);
+            const float bias = bias_r[m];
             if (!last) {
               if (MODE == 0) {
 #pragma unroll

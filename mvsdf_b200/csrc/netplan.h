@@ -19,11 +19,14 @@ constexpr int kChunkK = 32;        // K elements per pipeline stage
 constexpr int kStages = 4;
 constexpr int kTileBytes = kTileM * kChunkK * 2;   // 8 KiB (hi or lo)
 constexpr int kStageBytes = 2 * kTileBytes;        // 16 KiB
-constexpr int kBCoreStride = 8 * 128 + 16;         // 1040: byte stride between K-cores of the activation operand
+// Activation operand: per 8-wide K core, 16 groups of 8 columns x 16 B: groups 0-7 hold the fp16 hi parts of the 64
+// columns, groups 8-15 the lo parts, so that one N=128 UMMA multiplies W_hi with [X_hi ; X_lo] at full tensor rate.
+constexpr int kBLoOffset = 8 * 128;                // byte offset of the lo half inside a K core block
+constexpr int kBCoreStride = 16 * 128 + 16;        // 2064: +16 B so the epilogue's 2-byte stores spread over banks
 constexpr float kWeightScale = 64.0f;              // power of two: keeps the lo parts out of fp16 subnormals
 constexpr float kActScale = 64.0f;
 constexpr int kMaxLayers = 12;
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;                     // 4 output tiles x (64 + 64) accumulator columns
 
 enum Act : int { ACT_NONE = 0, ACT_SOFTPLUS100 = 1, ACT_RELU = 2 };
 enum NetKind : int { NET_SDF = 0, NET_RENDER = 1 };

@@ -60,6 +60,12 @@ __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void
       "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask)
       : "memory");
 }
+// one lane of the (converged) warp gets true
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
