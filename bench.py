@@ -109,7 +109,7 @@ GT_KEYS = ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center"]
 
 def run_ours(args):
     import torch.distributed as dist
-    from mvsdf_b200 import _lib
+    from mvsdf_b200 import _lib, parallel
     from mvsdf_b200.loss import B200IDRLoss
     from mvsdf_b200.network import B200IDRNetwork, default_conf
 
@@ -138,7 +138,7 @@ def run_ours(args):
 
     def reduce_fn(partial):
         if world > 1:
-            dist.all_reduce(partial, op=dist.ReduceOp.SUM)     # the single NCCL collective of the path
+            parallel.allreduce_partials(partial)                # NCCL all-reduce(SUM) of the loss partials
 
     host = pin({k: scene[k] for k in IN_KEYS + GT_KEYS})
     resident = {k: host[k].to(dev) for k in IN_KEYS + GT_KEYS}
@@ -272,7 +272,7 @@ def cpu_reference_sample(cfg, scene, sd, budget_s=20.0, threads=None):
     sw, rw = O.sdf_weights(sd), O.render_weights(sd)
     N = scene["uv"].shape[1]
     # calibrate: ~60 evals/ray * 2 * MACs at ~25 GFLOP/s/core-ish -> pick a sample, then rescale once
-    n_sample = min(N, 1024 if cfg["width"] >= 512 else 4096)
+    n_sample = min(N, 128 if cfg["width"] >= 512 else 1024)
     warm = dict(scene)
     warm["uv"] = scene["uv"][:, :64].contiguous()
     warm["object_mask"] = scene["object_mask"][:, :64].contiguous()
@@ -292,7 +292,7 @@ def cpu_reference_sample(cfg, scene, sd, budget_s=20.0, threads=None):
         n_done = sub["uv"].shape[0] * sub["uv"].shape[1]
         if dt >= 0.4 * budget_s or n_sample >= N:
             break
-        n_sample = int(min(N, n_sample * min(8.0, 0.8 * budget_s / max(dt, 1e-3))))
+        n_sample = int(min(N, n_sample * min(8.0, max(1.5, 0.8 * budget_s / max(dt, 1e-3)))))
     return {"value": n_done / dt, "unit": "rays/s", "cores": threads, "kind": "port",
             "sample": f"{n_done} rays (regular sub-grid of the {cfg['H']}x{cfg['W']} image, same weights/cameras/features), "
                       f"eval forward + feat loss + rgb L1 in {dt:.1f} s; oracle/mvsdf_oracle.py (PyTorch CPU restatement "

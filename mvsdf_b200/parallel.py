@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing of the hot path: rays are independent, so ranks take
+contiguous ray ranges *within each image* (the per-image grouping of get_feat_loss_corr, loss.py:120-123,
+stays local), weights and feature maps are replicated, and the only exchange is ONE all-reduce(SUM) of the
+loss partials -- rgb (sum, n_rays) and per-image feature (sum, count) -- after which every rank forms the
+scalars exactly like loss.py:27 and :155-163.  torch.distributed (NCCL on GPUs, gloo in the CPU tests)
+is only the transport."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.distributed as dist
+
+RAY_KEYS = ("uv", "object_mask", "rgb")
+
+
+def shard_bounds(n_pixels: int, rank: int, world: int):
+    """[begin, end) of the rank's contiguous slice of one image's rays (remainder spread over the first ranks)."""
+    base, rem = divmod(n_pixels, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_rays(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Per-image ray slices for this rank; everything that is not per-ray is replicated."""
+    n = batch["uv"].shape[1]
+    b, e = shard_bounds(n, rank, world)
+    out = dict(batch)
+    for k in RAY_KEYS:
+        if k in batch:
+            out[k] = batch[k][:, b:e].contiguous()
+    return out
+
+
+def allreduce_partials(*partials: torch.Tensor, group=None) -> None:
+    """The single collective of the path: SUM over ranks, in place, one flat buffer."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([p.reshape(-1) for p in partials])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in partials:
+        p.copy_(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()
+
+
+def finalize_rgb(partial: torch.Tensor) -> torch.Tensor:
+    """partial = (sum |rgb-gt| over hits, n_rays)  ->  loss.py:27."""
+    return (partial[0] / partial[1]).to(torch.float32) if float(partial[1]) > 0 else torch.zeros((), dtype=torch.float32)
+
+
+def finalize_feat(partials: torch.Tensor) -> torch.Tensor:
+    """partials [B,2] = (sum of kept |1-corr|, (V-1) m_i)  ->  mean over images of per-image means (loss.py:155-163)."""
+    s, c = partials[:, 0], partials[:, 1]
+    per_image = torch.where(c > 0, s / c.clamp_min(1), torch.zeros_like(s)).to(torch.float32)
+    return per_image.sum() / partials.shape[0]

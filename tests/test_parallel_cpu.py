@@ -1,0 +1,65 @@
+"""world_size-2 gloo test of the multi-GPU host logic (ray sharding + the single all-reduce of loss
+partials + finalisation).  The per-rank partials are produced by the CPU oracle here (no GPU in this
+container); on the GPU box the same reduction is fed by mvsdf_feat_loss_partials / mvsdf_rgb_l1_partials
+(tests/test_gpu_pipeline.py::test_shard_invariance_of_loss_partials)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mvsdf_b200 import parallel, synth
+    from oracle import mvsdf_oracle as O
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    sw, rw = O.sdf_weights(sd), O.render_weights(sd)
+    scene = synth.make_scene(20, 20, n_images=2, n_src=2, seed=6)
+    part = parallel.shard_rays(scene, rank, world)
+    with torch.no_grad():
+        out = O.idr_forward(sw, rw, part, None, False)
+    nm, om = out["network_object_mask"], out["object_mask"]
+    m = nm & om
+    rgb_p = torch.tensor([float((out["rgb_values"][m] - part["rgb"].reshape(-1, 3)[m]).abs().sum()), float(m.numel())],
+                         dtype=torch.float64)
+    _, parts = O.feat_loss_corr(out["diff_surf_pts"], part["feat"], part["cam"], part["feat_src"], part["src_cams"],
+                                part["size"][:1], part["center"][:1], nm, om, return_parts=True)
+    feat_p = torch.tensor(parts if parts else [(0.0, 0)] * 2, dtype=torch.float64)
+    parallel.allreduce_partials(rgb_p, feat_p)
+    if rank == 0:
+        ret["rgb"] = float(parallel.finalize_rgb(rgb_p))
+        ret["feat"] = float(parallel.finalize_feat(feat_p))
+    dist.destroy_process_group()
+
+
+def test_two_rank_loss_reduction_matches_unsharded():
+    sys.path.insert(0, ROOT)
+    from mvsdf_b200 import parallel, synth
+    from oracle import mvsdf_oracle as O
+    # shard bounds cover the range exactly once
+    for n, w in [(10, 3), (4096, 8), (7, 8)]:
+        covered = []
+        for r in range(w):
+            b, e = parallel.shard_bounds(n, r, w)
+            covered += list(range(b, e))
+        assert covered == list(range(n))
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    scene = synth.make_scene(20, 20, n_images=2, n_src=2, seed=6)
+    with torch.no_grad():
+        out = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), scene, None, False)
+    ref = O.hot_path_losses(out, scene, 0.5)
+    assert abs(ret["rgb"] - float(ref["rgb_loss"])) < 1e-6
+    assert abs(ret["feat"] - float(ref["feat_loss"])) < 1e-6
