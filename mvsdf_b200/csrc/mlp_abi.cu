@@ -12,7 +12,7 @@
 
 #include "../../include/mvsdf_b200.h"
 #include "internal.h"
-#include "mlp_kernel.cuh"
+#include "mlp_pair_kernel.cuh"
 
 struct mvsdf_net {
   mvsdf::NetPlan plan;
@@ -213,6 +213,25 @@ static int launch_mlp_cl(const NetPlan& p, MlpArgs& a, long long tiles, bool dev
   return rc;
 }
 
+// CTA-pair kernel (cta_group::2): 74 pairs, each walks 128-column tiles
+template <int KIND, int MODE>
+static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, bool device_count, cudaStream_t st) {
+  const int sms = sm_count();
+  const size_t smem = mlp_smem_bytes(p.k_cores_max);
+  auto kern = mlp_pair_kernel<KIND, MODE>;
+  int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "cudaFuncSetAttribute(mlp_pair_kernel)");
+  if (rc) return rc;
+  const int max_pairs = sms / 2;
+  const int n_pairs = device_count ? max_pairs : (int)std::min<long long>(pair_tiles, max_pairs);
+  const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : 0));
+  ProfEvent* pe = prof_begin(kind, st);
+  note_launch();
+  kern<<<2 * n_pairs, kMlpThreads, smem, st>>>(a);
+  prof_end(pe, st);
+  return check_cuda(cudaGetLastError(), "launch mlp_pair_kernel");
+}
+
 template <int KIND, int MODE>
 static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_dev, cudaStream_t st) {
   if (sm_count() <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
@@ -226,6 +245,8 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
   // small host-known batches cannot fill clusters: fall back to single-CTA scheduling (same kernel, CL = 1)
   const bool small = n_dev == nullptr && tiles < 2 * sm_count();
+  static const int pair = env_int("MVSDF_PAIR", 1);
+  if (pair && !small) return launch_mlp_pair<KIND, MODE>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
   if (cl >= 4 && !small) return launch_mlp_cl<KIND, MODE, 4>(p, a, tiles, n_dev != nullptr, st);
   if (cl >= 2 && !small) return launch_mlp_cl<KIND, MODE, 2>(p, a, tiles, n_dev != nullptr, st);
   return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, n_dev != nullptr, st);
