@@ -6,8 +6,8 @@
 //
 //   * weights: streamed from L2 as pre-tiled fp16 hi/lo pairs by 1-D bulk async copies (TMA engine)
 //     through a 4-stage mbarrier ring (warp 8);
-//   * activations: resident in shared memory as fp16 hi/lo pairs (K-major, un-swizzled core matrices,
-//     padded K-core stride so the epilogue's 2-byte stores are bank-conflict free);
+//   * activations: resident in shared memory as fp16 hi/lo pairs, MN-major un-swizzled core matrices: a thread
+//     of the epilogue owns one feature and consecutive columns, so it writes 16-byte vectors;
 //   * 3 UMMAs per K step (hi*hi + lo*hi + hi*lo) give ~22-bit operands with fp32 accumulation in
 //     TMEM -- the reference's fp32 SGEMM accuracy (SURVEY.md fact 0.9 rules out plain TF32/BF16);
 //   * epilogue (warps 0-15): as soon as the UMMAs of one 128-row output tile have committed (one mbarrier
@@ -70,7 +70,7 @@ __host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
 
 // byte offset of (column n, feature k) inside an activation operand buffer
 __device__ __forceinline__ uint32_t xoff(int n, int k) {
-  return (uint32_t)((k >> 3) * kBCoreStride + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+  return (uint32_t)((k >> 3) * kBCoreStride + (n >> 3) * 128 + (k & 7) * 16 + (n & 7) * 2);
 }
 
 __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, float v) {
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
     // Per 16-wide K step:  D[:, 0:128] += W_hi * [X_hi ; X_lo]^T   (N = 128: full tensor rate)
     //                      D[:, 0:64]  += W_lo * X_hi^T            (N = 64)
     // the epilogue adds the two 64-column halves, giving W_hi X_hi + W_lo X_hi + W_hi X_lo.
-    constexpr uint32_t idesc128 = ptx::idesc_f16_f32(kTileM, 2 * kTileN);
-    constexpr uint32_t idesc64 = ptx::idesc_f16_f32(kTileM, kTileN);
+    constexpr uint32_t idesc128 = ptx::idesc_f16_f32_bmn(kTileM, 2 * kTileN);
+    constexpr uint32_t idesc64 = ptx::idesc_f16_f32_bmn(kTileM, kTileN);
     const bool leader = ptx::elect_one();
     uint32_t it = 0, act_ctr = 0;
     for (long long g = group0; g < n_groups; g += group_stride) {
@@ -432,26 +432,27 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
           for (int m = 0; m < kMaxTiles; ++m) {
             if (m < lp.m_tiles) {
               const int f = m * kTileM + row;
-              const uint32_t o0 = xoff(cg * 16, f);
+              const uint32_t o0 = xoff(cg * 16, f);          // my 16 columns = two 16-byte vectors (8 columns each)
               if (skip_src && f >= a.skip_rows_begin) {
                 // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
                 const int k = f - a.skip_rows_begin;
                 const uint32_t s0 = xoff(cg * 16, k);
                 const bool real = k < a.pe_dim;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const uint32_t d = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);
-                  ptx::st_shared_u16(s_xhi + o0 + d, real ? ptx::ld_shared_u16(s_pehi + s0 + d) : (uint16_t)0);
-                  ptx::st_shared_u16(s_xlo + o0 + d, real ? ptx::ld_shared_u16(s_pelo + s0 + d) : (uint16_t)0);
+                for (int j = 0; j < 2; ++j) {
+                  uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+                  if (real) {
+                    vh = ptx::ld_shared_v4(s_pehi + s0 + j * 128);
+                    vl = ptx::ld_shared_v4(s_pelo + s0 + j * 128);
+                  }
+                  ptx::st_shared_v4(s_xhi + o0 + j * 128, vh.x, vh.y, vh.z, vh.w);
+                  ptx::st_shared_v4(s_xlo + o0 + j * 128, vl.x, vl.y, vl.z, vl.w);
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const uint32_t d = (uint32_t)(((2 * i) >> 3) * 128 + ((2 * i) & 7) * 16);
-                  ptx::st_shared_u16(s_xhi + o0 + d, (uint16_t)(phi[m][i] & 0xffffu));
-                  ptx::st_shared_u16(s_xhi + o0 + d + 16, (uint16_t)(phi[m][i] >> 16));
-                  ptx::st_shared_u16(s_xlo + o0 + d, (uint16_t)(plo[m][i] & 0xffffu));
-                  ptx::st_shared_u16(s_xlo + o0 + d + 16, (uint16_t)(plo[m][i] >> 16));
+                for (int j = 0; j < 2; ++j) {
+                  ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[m][4 * j], phi[m][4 * j + 1], phi[m][4 * j + 2], phi[m][4 * j + 3]);
+                  ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[m][4 * j], plo[m][4 * j + 1], plo[m][4 * j + 2], plo[m][4 * j + 3]);
                 }
               }
             }

@@ -98,7 +98,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   } else if (warp == kEpiWarps + 1) {
     if (crank == 0) {
       // ------------------------------------------------------------------ UMMA issuer (leader CTA)
-      constexpr uint32_t idesc = ptx::idesc_f16_f32(2 * kTileM, kPairCols);
+      constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, kPairCols);
       const bool leader = ptx::elect_one();
       uint32_t it = 0, act_ctr = 0;
       for (long long g = pair0; g < n_tiles; g += pair_stride) {
@@ -364,20 +364,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
               const int f = m * kTileM + row;
               const bool write = m < lp.m_tiles && !(skip_src && f >= a.skip_rows_begin);
               if (write) {
-                const uint32_t o0 = xoff(lcol0, f);
+                const uint32_t o0 = xoff(lcol0, f);          // my 32 columns = four 16-byte vectors
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const uint32_t d = (uint32_t)(((2 * i) >> 3) * 128 + ((2 * i) & 7) * 16);
+                for (int j = 0; j < 4; ++j) {
                   if (!remote) {
-                    ptx::st_shared_u16(s_xhi + o0 + d, (uint16_t)(phi[mp][i] & 0xffffu));
-                    ptx::st_shared_u16(s_xhi + o0 + d + 16, (uint16_t)(phi[mp][i] >> 16));
-                    ptx::st_shared_u16(s_xlo + o0 + d, (uint16_t)(plo[mp][i] & 0xffffu));
-                    ptx::st_shared_u16(s_xlo + o0 + d + 16, (uint16_t)(plo[mp][i] >> 16));
+                    ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
+                    ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
                   } else {
-                    ptx::st_cluster_u16(dst_xhi + o0 + d, (uint16_t)(phi[mp][i] & 0xffffu));
-                    ptx::st_cluster_u16(dst_xhi + o0 + d + 16, (uint16_t)(phi[mp][i] >> 16));
-                    ptx::st_cluster_u16(dst_xlo + o0 + d, (uint16_t)(plo[mp][i] & 0xffffu));
-                    ptx::st_cluster_u16(dst_xlo + o0 + d + 16, (uint16_t)(plo[mp][i] >> 16));
+                    ptx::st_cluster_v4(dst_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
+                    ptx::st_cluster_v4(dst_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
                   }
                 }
               }
@@ -386,11 +381,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           if (skip_src) {
             // skip connection: features [skip_rows_begin, +pe_dim) of MY 64 columns are the positional encoding
             // (already scaled and split in my PE tile) -- each CTA fills them for its own columns
-            for (int cidx = t; cidx < a.pe_dim * kTileN; cidx += kEpiThreads) {
-              const int k = cidx >> 6, col = cidx & 63;
-              const uint32_t so = xoff(col, k), dofs = xoff(col, a.skip_rows_begin + k);
-              ptx::st_shared_u16(s_xhi + dofs, ptx::ld_shared_u16(s_pehi + so));
-              ptx::st_shared_u16(s_xlo + dofs, ptx::ld_shared_u16(s_pelo + so));
+            for (int cidx = t; cidx < a.pe_dim * 16; cidx += kEpiThreads) {
+              const int k = cidx >> 4, blk = cidx & 15;           // 16 column blocks of 16 bytes per feature: 8 hi + 8 lo
+              const int kd = a.skip_rows_begin + k;
+              const uint4 v = ptx::ld_shared_v4(s_pehi + (uint32_t)((k >> 3) * kBCoreStride + (k & 7) * 16 + blk * 128));
+              ptx::st_shared_v4(s_xhi + (uint32_t)((kd >> 3) * kBCoreStride + (kd & 7) * 16 + blk * 128), v.x, v.y, v.z, v.w);
             }
           }
           ptx::tc_fence_before();

@@ -19,10 +19,13 @@ constexpr int kChunkK = 32;        // K elements per pipeline stage
 constexpr int kStages = 4;
 constexpr int kTileBytes = kTileM * kChunkK * 2;   // 8 KiB (hi or lo)
 constexpr int kStageBytes = 2 * kTileBytes;        // 16 KiB
-// Activation operand: per 8-wide K core, 16 groups of 8 columns x 16 B: groups 0-7 hold the fp16 hi parts of the 64
-// columns, groups 8-15 the lo parts, so that one N=128 UMMA multiplies W_hi with [X_hi ; X_lo] at full tensor rate.
-constexpr int kBLoOffset = 8 * 128;                // byte offset of the lo half inside a K core block
-constexpr int kBCoreStride = 16 * 128 + 16;        // 2064: +16 B so the epilogue's 2-byte stores spread over banks
+// Activation operand (B of the UMMA), MN-major / SWIZZLE_NONE: element (column n, feature k) lives at
+//   (k/8)*kBCoreStride + (n/8)*128 + (k%8)*16 + (n%8)*2
+// i.e. per block of 8 features: 16 column blocks of 128 B -- blocks 0-7 hold the fp16 hi parts of the 64 columns,
+// blocks 8-15 the lo parts (one N=128 descriptor covers [X_hi ; X_lo]).  A thread of the epilogue owns one feature and
+// consecutive columns, so its outputs are contiguous 16-byte vectors.
+constexpr int kBLoOffset = 8 * 128;                // byte offset of the lo half inside a feature block
+constexpr int kBCoreStride = 16 * 128;             // 2048: byte stride between blocks of 8 features (the descriptor's LBO)
 constexpr float kWeightScale = 64.0f;              // power of two: keeps the lo parts out of fp16 subnormals
 constexpr float kActScale = 64.0f;
 constexpr int kMaxLayers = 12;

@@ -10,7 +10,7 @@ using namespace mvsdf;
 
 constexpr int M = 128, N = 64, K = 16;
 
-__global__ void probe(const __half* A, const __half* B, float* D, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int swap_fields) {
+__global__ void probe(const __half* A, const __half* B, float* D, int a_lbo, int a_sbo, int b_lbo, int b_sbo, int swap_fields, int b_mn) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t s0 = ptx::smem_u32(smem);
   const uint32_t sA = s0, sB = s0 + 16384, sBar = s0 + 16384 + 16384, sT = sBar + 16;
@@ -21,7 +21,8 @@ __global__ void probe(const __half* A, const __half* B, float* D, int a_lbo, int
   }
   for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
     int n = i / K, k = i % K;
-    *reinterpret_cast<__half*>(smem + 16384 + (n / 8) * b_sbo + (k / 8) * b_lbo + (n % 8) * 16 + (k % 8) * 2) = B[i];
+    if (b_mn) *reinterpret_cast<__half*>(smem + 16384 + (n / 8) * b_sbo + (k / 8) * b_lbo + (k % 8) * 16 + (n % 8) * 2) = B[i];
+    else *reinterpret_cast<__half*>(smem + 16384 + (n / 8) * b_sbo + (k / 8) * b_lbo + (n % 8) * 16 + (k % 8) * 2) = B[i];
   }
   if (threadIdx.x == 0) { ptx::mbar_init(sBar, 1); ptx::fence_mbar_init(); }
   if (threadIdx.x < 32) { ptx::tmem_alloc(sT, 64); ptx::tmem_relinquish(); }
@@ -33,7 +34,7 @@ __global__ void probe(const __half* A, const __half* B, float* D, int a_lbo, int
   if (threadIdx.x == 0) {
     uint64_t da = swap_fields ? ptx::smem_desc(sA, a_sbo, a_lbo) : ptx::smem_desc(sA, a_lbo, a_sbo);
     uint64_t db = swap_fields ? ptx::smem_desc(sB, b_sbo, b_lbo) : ptx::smem_desc(sB, b_lbo, b_sbo);
-    ptx::umma_f16(tmem, da, db, ptx::idesc_f16_f32(M, N), 0u);
+    ptx::umma_f16(tmem, da, db, ptx::idesc_f16_f32(M, N) | (b_mn ? (1u << 16) : 0u), 0u);
     ptx::umma_commit(sBar);
   }
   ptx::mbar_wait(sBar, 0);
@@ -64,15 +65,17 @@ int main() {
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
-  struct V { int a_lbo, a_sbo, b_lbo, b_sbo, swap; const char* name; } vs[] = {
+  struct V { int a_lbo, a_sbo, b_lbo, b_sbo, swap; const char* name; int b_mn; } vs[] = {
       {128, 512, 1040, 128, 0, "design (A lbo128 sbo512, B lbo1040 sbo128)"},
       {128, 512, 1040, 128, 1, "design, descriptor fields swapped"},
       {128, 256, 128, 256, 0, "compact 2-core rows"},
       {2048, 128, 1024, 128, 0, "k-core-major A"},
+      {128, 512, 2048, 128, 0, "B MN-major (lbo 2048 = K blocks, sbo 128 = MN blocks)", 1},
+      {128, 512, 128, 2048, 0, "B MN-major, roles swapped (lbo 128, sbo 2048)", 1},
   };
   for (auto& v : vs) {
     cudaMemset(dD, 0, out.size() * 4);
-    probe<<<1, 128, 40000>>>(dA, dB, dD, v.a_lbo, v.a_sbo, v.b_lbo, v.b_sbo, v.swap);
+    probe<<<1, 128, 40000>>>(dA, dB, dD, v.a_lbo, v.a_sbo, v.b_lbo, v.b_sbo, v.swap, v.b_mn);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", v.name, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost);
