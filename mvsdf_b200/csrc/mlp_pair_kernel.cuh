@@ -105,7 +105,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         for (int l = 0; l < a.n_run; ++l) {
           const LayerPlan& lp = a.L[l];
           const int n_pair_tiles = (lp.m_tiles + 1) >> 1;
-          ptx::mbar_wait_cluster(bar_act, act_ctr & 1);
+          ptx::mbar_wait(bar_act, act_ctr & 1);
           ++act_ctr;
           ptx::tc_fence_after();
           const uint32_t b_base = lp.b_from_pe ? s_pehi : s_xhi;
@@ -115,7 +115,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             for (int kc = 0; kc < lp.k_chunks; ++kc, ++it) {
               const uint32_t s = it % kStages, ph = (it / kStages) & 1;
               ptx::mbar_wait(bar_full + 8 * s, ph);
-              ptx::mbar_wait_cluster(bar_full2 + 8 * s, ph);
+              ptx::mbar_wait(bar_full2 + 8 * s, ph);
               ptx::tc_fence_after();
               const uint32_t a_hi = s_stage + s * kStageBytes;
               const uint32_t a_lo = a_hi + kTileBytes;
@@ -152,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           for (int i = 0; i < n_stage; ++i, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             ptx::mbar_wait(bar_full + 8 * s, ph);
-            if (lane == 0) ptx::mbar_arrive_cluster(remote_full2 + 8 * s);
+            if (lane == 0) ptx::mbar_arrive_remote_relaxed(remote_full2 + 8 * s);
             __syncwarp();
           }
         }
@@ -257,9 +257,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_all();
-      ptx::fence_acq_rel_cluster();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(remote_act);
+      if (lane == 0) ptx::mbar_arrive_cluster(remote_act);      // release.cluster: publishes the warp's (remote) writes
 
       // ---------------- layers
       for (int l = 0; l < a.n_run; ++l) {
@@ -390,7 +389,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           }
           ptx::tc_fence_before();
           ptx::fence_proxy_async_all();
-          ptx::fence_acq_rel_cluster();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(remote_act);
         }

@@ -88,6 +88,10 @@ __device__ __forceinline__ void st_cluster_u16(uint32_t cluster_addr, uint16_t v
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// relay-style arrive with no data to publish (the data was written by the async proxy and tracked by the mbarrier)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
