@@ -116,7 +116,7 @@ __device__ __forceinline__ float softplus100_scaled_grad(float z, float& sig) {
 }
 
 template <int KIND, int MODE, int CL>
-__global__ void __maxnreg__(112) mlp_tile_kernel(const MlpArgs a) {
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -20,7 +20,7 @@ constexpr int kPairTiles = 2;          // 256-row tiles per layer (width <= 512)
 constexpr int kPairCols = 2 * kTileN;  // 128 columns per pair tile
 
 template <int KIND, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) mlp_pair_kernel(const MlpArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_pair_kernel(const MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -272,10 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) mlp_pair_kernel(const
           const int m = 2 * mp + (int)crank;
           bias_r[mp] = m < lp.m_tiles ? __ldg(a.bias + lp.bias_off + m * kTileM + row) : 0.f;
         }
-        // Outputs of pair tile 0 are parked in registers while the tensor cores work on tile 1 (in-place hazard: the
-        // activation operand may only be overwritten once every UMMA of the layer has retired); the last tile of the
-        // layer is stored chunk by chunk straight away -- its barrier implies that all UMMAs are done.
-        uint32_t park_hi[16], park_lo[16];
+        uint32_t phi[kPairTiles][16], plo[kPairTiles][16];
 #pragma unroll
         for (int mp = 0; mp < kPairTiles; ++mp) {
           if (mp < n_pair_tiles) {
@@ -286,19 +283,14 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) mlp_pair_kernel(const
             const int f = m * kTileM + row;                 // feature (output row) this thread owns
             const bool have = m < lp.m_tiles;
             const float bias = bias_r[mp];
-            const bool park = !last && (mp + 1 < n_pair_tiles);
-            const bool writable = have && !(skip_src && f >= a.skip_rows_begin);
-            const uint32_t o0 = xoff(lcol0, f);              // my 32 columns = four 16-byte vectors
+            uint32_t vv[2][16];
+            ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * kPairCols), vv[0]);
+            ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * kPairCols + 16), vv[1]);
+            ptx::tmem_ld_wait();
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {           // two 16-column halves of my 32 columns
-              uint32_t v[16], v2[16];
-              ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kPairCols + hcol * 16), v);
-              ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kPairCols + kPairCols + hcol * 16), v2);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+              uint32_t(&v)[16] = vv[hcol];
               if (!last) {
-                uint32_t ph[8], pl[8];
                 if (MODE == 0) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
@@ -306,7 +298,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) mlp_pair_kernel(const
                     const float z1 = fmaf(__uint_as_float(v[2 * i + 1]), kInvScale, bias);
                     const float y0 = (KIND == NET_SDF) ? softplus100_scaled(z0) : fmaxf(z0, 0.0f) * kActScale;
                     const float y1 = (KIND == NET_SDF) ? softplus100_scaled(z1) : fmaxf(z1, 0.0f) * kActScale;
-                    pack_split(y0, y1, ph[i], pl[i]);
+                    pack_split(y0, y1, phi[mp][hcol * 8 + i], plo[mp][hcol * 8 + i]);
                   }
                 } else {
 #pragma unroll
@@ -315,29 +307,9 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) mlp_pair_kernel(const
                     float sg;
                     const float y = softplus100_scaled_grad(z, sg);
                     const float ts = sg * (kInvScale * kActScale);
-                    pack_split(y, __uint_as_float(v[4 * gq + 1]) * ts, ph[2 * gq], pl[2 * gq]);
-                    pack_split(__uint_as_float(v[4 * gq + 2]) * ts, __uint_as_float(v[4 * gq + 3]) * ts, ph[2 * gq + 1], pl[2 * gq + 1]);
-                  }
-                }
-                if (park) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    park_hi[hcol * 8 + i] = ph[i];
-                    park_lo[hcol * 8 + i] = pl[i];
-                  }
-                } else if (writable) {
-                  // every UMMA of the layer has retired in both CTAs: overwrite the activation operand in place; rows
-                  // for the peer's columns go straight into the peer's shared memory
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    const uint32_t o = o0 + (uint32_t)((hcol * 2 + j) * 128);
-                    if (!remote) {
-                      ptx::st_shared_v4(s_xhi + o, ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                      ptx::st_shared_v4(s_xlo + o, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    } else {
-                      ptx::st_cluster_v4(dst_xhi + o, ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                      ptx::st_cluster_v4(dst_xlo + o, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    }
+                    pack_split(y, __uint_as_float(v[4 * gq + 1]) * ts, phi[mp][hcol * 8 + 2 * gq], plo[mp][hcol * 8 + 2 * gq]);
+                    pack_split(__uint_as_float(v[4 * gq + 2]) * ts, __uint_as_float(v[4 * gq + 3]) * ts,
+                               phi[mp][hcol * 8 + 2 * gq + 1], plo[mp][hcol * 8 + 2 * gq + 1]);
                   }
                 }
               } else if (have) {
@@ -377,27 +349,32 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112) mlp_pair_kernel(const
                 }
               }
             }
-            if (!last && !park && mp > 0) {
-              // the parked outputs of the previous pair tile
-              const int mprev = 2 * (mp - 1) + (int)crank;
-              const int fprev = mprev * kTileM + row;
-              if (mprev < lp.m_tiles && !(skip_src && fprev >= a.skip_rows_begin)) {
-                const uint32_t op = xoff(lcol0, fprev);
+          }
+        }
+        if (!last) {
+          // all UMMAs of the layer have retired in both CTAs: overwrite the activation operands in place,
+          // my rows for the peer's columns go straight into the peer's shared memory
+#pragma unroll
+          for (int mp = 0; mp < kPairTiles; ++mp) {
+            if (mp < n_pair_tiles) {
+              const int m = 2 * mp + (int)crank;
+              const int f = m * kTileM + row;
+              const bool write = m < lp.m_tiles && !(skip_src && f >= a.skip_rows_begin);
+              if (write) {
+                const uint32_t o0 = xoff(lcol0, f);          // my 32 columns = four 16-byte vectors
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   if (!remote) {
-                    ptx::st_shared_v4(s_xhi + op + j * 128, park_hi[4 * j], park_hi[4 * j + 1], park_hi[4 * j + 2], park_hi[4 * j + 3]);
-                    ptx::st_shared_v4(s_xlo + op + j * 128, park_lo[4 * j], park_lo[4 * j + 1], park_lo[4 * j + 2], park_lo[4 * j + 3]);
+                    ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
+                    ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
                   } else {
-                    ptx::st_cluster_v4(dst_xhi + op + j * 128, park_hi[4 * j], park_hi[4 * j + 1], park_hi[4 * j + 2], park_hi[4 * j + 3]);
-                    ptx::st_cluster_v4(dst_xlo + op + j * 128, park_lo[4 * j], park_lo[4 * j + 1], park_lo[4 * j + 2], park_lo[4 * j + 3]);
+                    ptx::st_cluster_v4(dst_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
+                    ptx::st_cluster_v4(dst_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
                   }
                 }
               }
             }
           }
-        }
-        if (!last) {
           if (skip_src) {
             // skip connection: features [skip_rows_begin, +pe_dim) of MY 64 columns are the positional encoding
             // (already scaled and split in my PE tile) -- each CTA fills them for its own columns
