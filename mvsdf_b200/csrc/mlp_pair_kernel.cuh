@@ -3,8 +3,8 @@
 // each CTA streams only its own 128-row half, so the per-SM weight stream and the per-SM shared-memory operand
 // traffic are half those of the single-CTA kernel for the same columns.
 //
-//   D[256 features (128 TMEM lanes per CTA), 128 columns] += W_hi [X_hi]^T + W_hi [X_lo]^T + W_lo [X_hi]^T
-//                                                             (3 UMMAs per K step, M=256 N=128 K=16, one accumulator)
+//   D[256 features (128 TMEM lanes per CTA), 128 columns]:
+//       D_a += W_hi [X_hi]^T      D_b += W_hi [X_lo]^T      D_a += W_lo [X_hi]^T          (3 UMMAs, M=256 N=128 K=16)
 //   X_hi / X_lo rows (columns of the tile) 0-63 come from CTA 0's shared memory, 64-127 from CTA 1's.
 //
 // The epilogue of CTA r owns features [256 mp + 128 r, +128) for all 128 columns: the half that belongs to the peer's
@@ -110,7 +110,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
           ptx::tc_fence_after();
           const uint32_t b_base = lp.b_from_pe ? s_pehi : s_xhi;
           for (int mp = 0; mp < n_pair_tiles; ++mp) {
-            const uint32_t d_acc = tmem_base + (uint32_t)(mp * kPairCols);
+            const uint32_t d_a = tmem_base + (uint32_t)(mp * 2 * kPairCols);
+            const uint32_t d_b = d_a + kPairCols;
             for (int kc = 0; kc < lp.k_chunks; ++kc, ++it) {
               const uint32_t s = it % kStages, ph = (it / kStages) & 1;
               ptx::mbar_wait(bar_full + 8 * s, ph);
@@ -127,9 +128,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 const uint64_t db_lo = ptx::smem_desc(b_base + kBLoOffset + boff, kBCoreStride, 128);
                 if (leader && !(a.debug & 2)) {
                   const uint32_t acc = (kc | ks) != 0 ? 1u : 0u;
-                  ptx::umma_f16_2cta(d_acc, da_hi, db_hi, idesc, acc);
-                  ptx::umma_f16_2cta(d_acc, da_hi, db_lo, idesc, 1u);
-                  ptx::umma_f16_2cta(d_acc, da_lo, db_hi, idesc, 1u);
+                  ptx::umma_f16_2cta(d_a, da_hi, db_hi, idesc, acc);
+                  ptx::umma_f16_2cta(d_b, da_hi, db_lo, idesc, acc);
+                  ptx::umma_f16_2cta(d_a, da_lo, db_hi, idesc, 1u);
                 }
               }
               if (leader) ptx::umma_commit_2cta(bar_empty + 8 * s, 3);
@@ -283,13 +284,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             const int f = m * kTileM + row;                 // feature (output row) this thread owns
             const bool have = m < lp.m_tiles;
             const float bias = bias_r[mp];
-            uint32_t vv[2][16];
-            ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * kPairCols), vv[0]);
-            ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * kPairCols + 16), vv[1]);
-            ptx::tmem_ld_wait();
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {           // two 16-column halves of my 32 columns
-              uint32_t(&v)[16] = vv[hcol];
+              uint32_t v[16], v2[16];
+              ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kPairCols + hcol * 16), v);
+              ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kPairCols + kPairCols + hcol * 16), v2);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
               if (!last) {
                 if (MODE == 0) {
 #pragma unroll
