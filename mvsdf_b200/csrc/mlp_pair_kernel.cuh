@@ -161,14 +161,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   } else {
     // ------------------------------------------------------------------ prologue + epilogue warps
     const int q = warp & 3;              // TMEM lane quarter
-    const int cg = warp >> 2;            // 32-column group of the 128-column tile: 0,1 -> CTA 0's columns, 2,3 -> CTA 1's
+    const int cg = warp >> 2;            // 16-column group: this warp produces columns [16cg,+16) of MY 64 columns
+                                         // (chunk 0, local stores) and of the PEER's 64 columns (chunk 1, DSMEM stores),
+                                         // so that every warp carries the same share of remote traffic
     const int row = q * 32 + lane;       // row inside my 128-row half
     const int t = threadIdx.x;
-    const uint32_t dest = (uint32_t)(cg >> 1);
-    const bool remote = dest != crank;
-    const int lcol0 = (cg & 1) * 32;     // first column (inside the destination CTA's 64) this warp produces
-    // base addresses of the destination activation buffer (cluster window when it is the peer's)
-    const uint32_t dst_xhi = ptx::mapa(s_xhi, dest);
+    const int lcol0 = cg * 16;           // first column inside the destination CTA's 64
+    // base addresses of the peer's activation buffer in the cluster window
+    const uint32_t dst_xhi = ptx::mapa(s_xhi, crank ^ 1u);
     const uint32_t dst_xlo = dst_xhi + kBLoOffset;
     const uint32_t remote_act = ptx::mapa(bar_act, 0);
     constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
@@ -265,7 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         const LayerPlan& lp = a.L[l];
         const bool last = (l == a.n_run - 1);
         const int n_pair_tiles = (lp.m_tiles + 1) >> 1;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool skip_src = KIND == NET_SDF && l == a.skip_layer - 1;
         float bias_r[kPairTiles];
 #pragma unroll
@@ -286,9 +286,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             const float bias = bias_r[mp];
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {           // two 16-column halves of my 32 columns
+              // chunk 0: my own columns, chunk 1: the peer's columns (columns 0-63 of the tile are CTA 0's)
+              const uint32_t dest_h = hcol == 0 ? crank : (crank ^ 1u);
+              const uint32_t tcol = (uint32_t)(mp * 2 * kPairCols) + dest_h * kTileN + (uint32_t)lcol0;
               uint32_t v[16], v2[16];
-              ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kPairCols + hcol * 16), v);
-              ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kPairCols + kPairCols + hcol * 16), v2);
+              ptx::tmem_ld_32x16(t_row + tcol, v);
+              ptx::tmem_ld_32x16(t_row + tcol + kPairCols, v2);
               ptx::tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
@@ -318,9 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 // ---------------- head: write results to global memory
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  const int col = cg * 32 + hcol * 16 + j;          // column of the 128-column pair tile
-                  // columns 0-63 are CTA 0's points, 64-127 CTA 1's
-                  const int ccta = col >> 6, lc = col & 63;
+                  const int ccta = (int)dest_h, lc = lcol0 + j;   // owner CTA of the column and its index there
                   const float acc = __uint_as_float(v[j]) * kInvScale;
                   if (KIND == NET_RENDER) {
                     const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;
@@ -363,16 +364,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
               const int f = m * kTileM + row;
               const bool write = m < lp.m_tiles && !(skip_src && f >= a.skip_rows_begin);
               if (write) {
-                const uint32_t o0 = xoff(lcol0, f);          // my 32 columns = four 16-byte vectors
+                const uint32_t o0 = xoff(lcol0, f);          // 16 local + 16 remote columns = 2 + 2 16-byte vectors (hi, lo each)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (!remote) {
-                    ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
-                    ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
-                  } else {
-                    ptx::st_cluster_v4(dst_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
-                    ptx::st_cluster_v4(dst_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
-                  }
+                for (int j = 0; j < 2; ++j) {
+                  ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[mp][4 * j], phi[mp][4 * j + 1], phi[mp][4 * j + 2], phi[mp][4 * j + 3]);
+                  ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[mp][4 * j], plo[mp][4 * j + 1], plo[mp][4 * j + 2], plo[mp][4 * j + 3]);
+                  ptx::st_cluster_v4(dst_xhi + o0 + j * 128, phi[mp][8 + 4 * j], phi[mp][8 + 4 * j + 1], phi[mp][8 + 4 * j + 2], phi[mp][8 + 4 * j + 3]);
+                  ptx::st_cluster_v4(dst_xlo + o0 + j * 128, plo[mp][8 + 4 * j], plo[mp][8 + 4 * j + 1], plo[mp][8 + 4 * j + 2], plo[mp][8 + 4 * j + 3]);
                 }
               }
             }

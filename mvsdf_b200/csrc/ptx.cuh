@@ -113,6 +113,10 @@ __device__ __forceinline__ void fence_acq_rel_cluster() {
 __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
+// shared-memory window of the whole cluster (own and peer CTA) only
+__device__ __forceinline__ void fence_proxy_async_cluster_smem() {
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
 // tcgen05 with cta_group::2: one thread of the leader CTA drives the tensor cores of both SMs of the pair
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
