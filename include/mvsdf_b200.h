@@ -92,7 +92,7 @@ typedef struct mvsdf_tracer_params {
   int skip_min_sdf;       /* training only: drop minimal_sdf_points (:280-308), whose outputs no MVSDF loss reads */
 } mvsdf_tracer_params;
 
-#define MVSDF_NUM_TRACE_COUNTERS 128
+#define MVSDF_NUM_TRACE_COUNTERS 256
 
 size_t mvsdf_trace_workspace_bytes(int64_t n_rays, int n_images);
 

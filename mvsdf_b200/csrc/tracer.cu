@@ -398,7 +398,7 @@ __global__ void trace_output_kernel(TraceCtx c, float* __restrict__ dists, uint8
   }
 }
 
-constexpr int kNumCounters = 128;
+constexpr int kNumCounters = 256;
 
 struct WorkspaceLayout {
   size_t off_counters, off_cam, off_f[9], off_i[4], off_flags, off_req_pts, off_req_val, total;

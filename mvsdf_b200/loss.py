@@ -88,6 +88,8 @@ class B200IDRLoss(nn.Module):
         _, V, h, w, C = maps.shape
         cams = torch.cat([cam.to(dev).unsqueeze(1), src_cams.to(dev)], dim=1).to(torch.float32).contiguous()   # [B,V,2,4,4]
         pts = ops._f32(diff_surf_pts)
+        if pts.numel() == 0:            # no surface point at all: the kernel reads M = 0 from hit_offsets and touches nothing
+            pts = torch.zeros(1, 3, dtype=torch.float32, device=dev)
         size = ops._f32(size.to(dev)).reshape(-1)[:1].contiguous()
         center = ops._f32(center.to(dev)).reshape(-1)[:3].contiguous()
         partial = torch.empty(B, 2, dtype=torch.float64, device=dev)

@@ -275,7 +275,7 @@ class B200IDRNetwork(nn.Module):
         dists = torch.empty(R, **f)
         net_mask = torch.empty(R, dtype=torch.uint8, device=dev)
         points = torch.empty(R, 3, **f)
-        counters = torch.empty(128, dtype=torch.int32, device=dev)
+        counters = torch.empty(256, dtype=torch.int32, device=dev)
         lin = torch.linspace(0, 1, steps=self.tracer_conf["n_steps"]).to(dev)        # ray_tracing.py:206
         steps = None
         if training and not self.skip_min_sdf:
