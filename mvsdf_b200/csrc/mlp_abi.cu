@@ -13,6 +13,7 @@
 #include "../../include/mvsdf_b200.h"
 #include "internal.h"
 #include "mlp_pair_kernel.cuh"
+#include "mlp_pair2_kernel.cuh"
 
 struct mvsdf_net {
   mvsdf::NetPlan plan;
@@ -214,11 +215,11 @@ static int launch_mlp_cl(const NetPlan& p, MlpArgs& a, long long tiles, bool dev
 }
 
 // CTA-pair kernel (cta_group::2): 74 pairs, each walks 128-column tiles
-template <int KIND, int MODE>
+template <int KIND, int MODE, int VER>
 static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, bool device_count, cudaStream_t st) {
   const int sms = sm_count();
   const size_t smem = mlp_smem_bytes(p.k_cores_max);
-  auto kern = mlp_pair_kernel<KIND, MODE>;
+  auto kern = VER == 2 ? mlp_pair2_kernel<KIND, MODE> : mlp_pair_kernel<KIND, MODE>;
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(mlp_pair_kernel)");
   if (rc) return rc;
@@ -245,8 +246,10 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
   // small host-known batches cannot fill clusters: fall back to single-CTA scheduling (same kernel, CL = 1)
   const bool small = n_dev == nullptr && tiles < 2 * sm_count();
-  static const int pair = env_int("MVSDF_PAIR", 1);
-  if (pair && !small) return launch_mlp_pair<KIND, MODE>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
+  // 2 = split-K pipelined pair kernel (default), 1 = layer-synchronous pair kernel, 0 = single-CTA kernel
+  static const int pair = env_int("MVSDF_PAIR", 2);
+  if (pair >= 2 && !small) return launch_mlp_pair<KIND, MODE, 2>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
+  if (pair && !small) return launch_mlp_pair<KIND, MODE, 1>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
   if (cl >= 4 && !small) return launch_mlp_cl<KIND, MODE, 4>(p, a, tiles, n_dev != nullptr, st);
   if (cl >= 2 && !small) return launch_mlp_cl<KIND, MODE, 2>(p, a, tiles, n_dev != nullptr, st);
   return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, n_dev != nullptr, st);

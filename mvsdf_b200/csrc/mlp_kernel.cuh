@@ -65,7 +65,7 @@ struct MlpArgs {
 };
 
 __host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
-  return (size_t)kStages * kStageBytes + (size_t)k_cores_max * kBCoreStride + kPeTileBytes + 128;
+  return (size_t)kStages * kStageBytes + (size_t)k_cores_max * kBCoreStride + kPeTileBytes + 256;
 }
 
 // byte offset of (column n, feature k) inside an activation operand buffer

@@ -1,0 +1,450 @@
+// CTA-pair MLP tile core, split-K pipelined ("pair2"): same data path as mlp_pair_kernel.cuh (cta_group::2 UMMAs,
+// M=256 x N=128 per pair tile, each CTA streams its 128-row half of every weight tile, epilogue exchange through
+// DSMEM) but the layer-to-layer dependency is tracked per HALF of the K dimension, so the tensor cores no longer
+// idle while the epilogue of a layer's last output tile runs.
+//
+// A 512-wide layer is a 2x2 block product   D_mp = W[mp][0] X[0] + W[mp][1] X[1]   (mp = 256-row pair tile,
+// X[h] = input features [256h, 256h+256)).  Epilogue stage E_mp turns D_mp into X'[mp] of the next layer.
+// UMMA order per layer:   (mp0,X0) (mp1,X0) (mp0,X1) | commit D_0 | (mp1,X1) | commit D_1
+//   * E_0 starts after 3/4 of the layer's UMMAs, and X[0] has been fully consumed by then, so E_0 overwrites
+//     X[0] in place as it goes (no register parking);
+//   * the next layer's (mp0,X'0) (mp1,X'0) only need E_0 (barrier bar_x0) and "D_1 drained to registers" (bar_d1);
+//     they run while E_1 produces X'[1] (barrier bar_x1).
+// Numerics, packed weights and epilogue math are those of mlp_kernel.cuh.
+#pragma once
+#include "mlp_kernel.cuh"
+
+namespace mvsdf {
+
+constexpr int kP2Tiles = 2;                 // 256-row pair tiles per layer (width <= 512)
+constexpr int kP2Cols = 2 * kTileN;         // 128 columns per pair tile
+constexpr int kP2SplitChunks = 256 / kChunkK;   // K chunks that belong to X[0]
+
+// part p of a layer: 0 = (mp0, X0), 1 = (mp1, X0), 2 = (mp0, X1), 3 = (mp1, X1)
+__device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, int& k0, int& k1, bool& run) {
+  const int n_pair_tiles = (lp.m_tiles + 1) >> 1;
+  const int ks = lp.k_chunks < kP2SplitChunks ? lp.k_chunks : kP2SplitChunks;
+  mp = part & 1;
+  k0 = part < 2 ? 0 : ks;
+  k1 = part < 2 ? ks : lp.k_chunks;
+  run = mp < n_pair_tiles && k0 < k1;
+}
+
+template <int KIND, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_pair2_kernel(const MlpArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const uint32_t xbytes = (uint32_t)a.k_cores_max * kBCoreStride;
+  const uint32_t s_stage = ptx::smem_u32(smem);
+  const uint32_t s_xhi = s_stage + kStages * kStageBytes;
+  const uint32_t s_xlo = s_xhi + kBLoOffset;
+  const uint32_t s_pehi = s_xhi + xbytes;
+  const uint32_t s_pelo = s_pehi + kBLoOffset;
+  const uint32_t s_bar = s_pehi + kPeTileBytes;
+  const uint32_t bar_full = s_bar;                        // kStages: my weight half has landed
+  const uint32_t bar_full2 = s_bar + 8 * kStages;         // kStages: (leader only) the peer's half has landed
+  const uint32_t bar_empty = s_bar + 16 * kStages;        // kStages: the UMMAs reading the stage retired (both CTAs)
+  const uint32_t bar_acc = s_bar + 24 * kStages;          // kP2Tiles: accumulators of pair tile mp complete (both CTAs)
+  const uint32_t bar_x = bar_acc + 8 * kP2Tiles;          // 2 (leader only): B operand half h written in BOTH CTAs
+  const uint32_t bar_d1 = bar_x + 16;                     // (leader only) accumulator 1 drained to registers in BOTH CTAs
+  const uint32_t s_tmem = bar_d1 + 8;
+  uint8_t* const g_scratch = (KIND == NET_SDF) ? (smem + kStages * kStageBytes) : (smem + kStages * kStageBytes + xbytes);
+  float* const scratch = reinterpret_cast<float*>(g_scratch);
+
+  const int n_dev_count = a.n_ptr ? __shfl_sync(0xffffffffu, *a.n_ptr, 0) : 0;
+  const long long n_pts = a.n_ptr ? (long long)n_dev_count : a.n;
+  constexpr int kPtsPerCta = (MODE == 0) ? kTileN : kTileN / 4;       // points per CTA per tile
+  const long long n_tiles = (n_pts + 2 * kPtsPerCta - 1) / (2 * kPtsPerCta);
+  const long long pair0 = blockIdx.x >> 1;
+  const long long pair_stride = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_full2 + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int m = 0; m < kP2Tiles; ++m) ptx::mbar_init(bar_acc + 8 * m, 1);
+    ptx::mbar_init(bar_x, 2 * kEpiWarps);
+    ptx::mbar_init(bar_x + 8, 2 * kEpiWarps);
+    ptx::mbar_init(bar_d1, 2 * kEpiWarps);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kEpiWarps + 1) {
+    ptx::tmem_alloc_2cta(s_tmem, kTmemCols);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - s_stage)), 0);
+
+  if (warp == kEpiWarps) {
+    // ------------------------------------------------------------------ weight producer: my 128-row half, in UMMA order
+    uint32_t it = 0;
+    for (long long g = pair0; g < n_tiles; g += pair_stride) {
+      for (int l = 0; l < a.n_run; ++l) {
+        const LayerPlan& lp = a.L[l];
+        for (int part = 0; part < 4; ++part) {
+          int mp, k0, k1;
+          bool run;
+          p2_part(lp, part, mp, k0, k1, run);
+          if (!run) continue;
+          const int m = 2 * mp + (int)crank;
+          const bool have = m < lp.m_tiles;
+          const uint8_t* src = a.packed + lp.w_off + (size_t)m * lp.k_chunks * kStageBytes;
+          for (int kc = k0; kc < k1; ++kc, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (lane == 0) {
+              if (have && !(a.debug & 1)) {
+                ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
+                ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)kc * kStageBytes, kStageBytes, bar_full + 8 * s);
+              } else {
+                ptx::mbar_arrive(bar_full + 8 * s);     // odd tile count: this half multiplies stale data into rows nobody reads
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    if (crank == 0) {
+      // ------------------------------------------------------------------ UMMA issuer (leader CTA)
+      constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, kP2Cols);
+      const bool leader = ptx::elect_one();
+      uint32_t it = 0, x_ctr = 0, d1_uses = 0;
+      for (long long g = pair0; g < n_tiles; g += pair_stride) {
+        for (int l = 0; l < a.n_run; ++l) {
+          const LayerPlan& lp = a.L[l];
+          const uint32_t b_base = lp.b_from_pe ? s_pehi : s_xhi;
+          for (int part = 0; part < 4; ++part) {
+            int mp, k0, k1;
+            bool run;
+            p2_part(lp, part, mp, k0, k1, run);
+            if (part == 0) {          // X[0] of this layer written by both CTAs (also: D_0 drained by the previous E_0)
+              ptx::mbar_wait_cluster(bar_x, x_ctr & 1);
+              ptx::tc_fence_after();
+            } else if (part == 2) {   // X[1] written
+              ptx::mbar_wait_cluster(bar_x + 8, x_ctr & 1);
+              ptx::tc_fence_after();
+              ++x_ctr;
+            }
+            if (!run) continue;
+            if (part == 1) {          // first write into D_1 this layer: its previous contents must have been read
+              if (d1_uses > 0) {
+                ptx::mbar_wait_cluster(bar_d1, (d1_uses - 1) & 1);
+                ptx::tc_fence_after();
+              }
+              ++d1_uses;
+            }
+            const uint32_t d_a = tmem_base + (uint32_t)(mp * 2 * kP2Cols);
+            const uint32_t d_b = d_a + kP2Cols;
+            for (int kc = k0; kc < k1; ++kc, ++it) {
+              const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+              ptx::mbar_wait(bar_full + 8 * s, ph);
+              ptx::mbar_wait(bar_full2 + 8 * s, ph);
+              ptx::tc_fence_after();
+              const uint32_t a_hi = s_stage + s * kStageBytes;
+              const uint32_t a_lo = a_hi + kTileBytes;
+#pragma unroll
+              for (int ks = 0; ks < kChunkK / 16; ++ks) {
+                const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 256, 128, 512);
+                const uint64_t da_lo = ptx::smem_desc(a_lo + ks * 256, 128, 512);
+                const uint32_t boff = (uint32_t)((kc * (kChunkK / 8) + ks * 2) * kBCoreStride);
+                const uint64_t db_hi = ptx::smem_desc(b_base + boff, kBCoreStride, 128);
+                const uint64_t db_lo = ptx::smem_desc(b_base + kBLoOffset + boff, kBCoreStride, 128);
+                if (leader && !(a.debug & 2)) {
+                  const uint32_t acc = (kc | ks) != 0 ? 1u : 0u;
+                  ptx::umma_f16_2cta(d_a, da_hi, db_hi, idesc, acc);
+                  ptx::umma_f16_2cta(d_b, da_hi, db_lo, idesc, acc);
+                  ptx::umma_f16_2cta(d_a, da_lo, db_hi, idesc, 1u);
+                }
+              }
+              if (leader) ptx::umma_commit_2cta(bar_empty + 8 * s, 3);
+              __syncwarp();
+            }
+            if (k1 == lp.k_chunks) {      // this part completes D_mp
+              if (leader) ptx::umma_commit_2cta(bar_acc + 8 * mp, 3);
+              __syncwarp();
+            }
+          }
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------ peer relay: tell the leader my stage has landed
+      const uint32_t remote_full2 = ptx::mapa(bar_full2, 0);
+      uint32_t it = 0;
+      for (long long g = pair0; g < n_tiles; g += pair_stride) {
+        for (int l = 0; l < a.n_run; ++l) {
+          const LayerPlan& lp = a.L[l];
+          const int n_stage = ((lp.m_tiles + 1) >> 1) * lp.k_chunks;
+          for (int i = 0; i < n_stage; ++i, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            ptx::mbar_wait(bar_full + 8 * s, ph);
+            if (lane == 0) ptx::mbar_arrive_remote_relaxed(remote_full2 + 8 * s);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ prologue + epilogue warps
+    const int q = warp & 3;              // TMEM lane quarter
+    const int cg = warp >> 2;            // 16-column group: this warp produces columns [16cg,+16) of MY 64 columns
+                                         // (local stores) and of the PEER's 64 columns (DSMEM stores)
+    const int row = q * 32 + lane;       // row inside my 128-row half
+    const int t = threadIdx.x;
+    const int lcol0 = cg * 16;           // first column inside the destination CTA's 64
+    const uint32_t dst_xhi = ptx::mapa(s_xhi, crank ^ 1u);   // the peer's activation buffer in the cluster window
+    const uint32_t dst_xlo = dst_xhi + kBLoOffset;
+    const uint32_t remote_x = ptx::mapa(bar_x, 0);
+    const uint32_t remote_d1 = ptx::mapa(bar_d1, 0);
+    constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
+    uint32_t acc_ctr[kP2Tiles] = {0, 0};
+
+    for (long long g = pair0; g < n_tiles; g += pair_stride) {
+      const long long p0 = g * (2 * kPtsPerCta) + (long long)crank * kPtsPerCta;      // my first point
+      const long long p0_pair = g * (2 * kPtsPerCta);
+
+      // ---------------- prologue: first layer's B operand for MY 64 columns (identical to the single-CTA kernel)
+      if (KIND == NET_SDF) {
+        if (t < 3 * kPtsPerCta) {
+          const int pt = t / 3, c = t - 3 * pt;
+          const long long gp = p0 + pt;
+          const float xc = gp < n_pts ? __ldg(a.x + gp * 3 + c) : 0.0f;
+          float* pe = scratch + pt * kScratchStride;
+          pe[c] = xc;
+          float* dpe = scratch + (kPtsPerCta + pt) * kScratchStride;
+          if (MODE == 1) dpe[c] = 1.0f;
+          float f = 1.0f;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            float sn, cs;
+            sincosf(xc * f, &sn, &cs);
+            pe[3 + 6 * i + c] = sn;
+            pe[6 + 6 * i + c] = cs;
+            if (MODE == 1) {
+              dpe[3 + 6 * i + c] = f * cs;
+              dpe[6 + 6 * i + c] = -f * sn;
+            }
+            f *= 2.0f;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        for (int cidx = t; cidx < kTileN * 64; cidx += kEpiThreads) {
+          const int col = cidx >> 6, k = cidx & 63;
+          float v = 0.0f;
+          if (k < a.pe_dim) {
+            if (MODE == 0) {
+              v = scratch[col * kScratchStride + k];
+            } else {
+              const int pt = col >> 2, j = col & 3;
+              const int coord = k < 3 ? k : (k - 3) % 3;
+              v = j == 0 ? scratch[pt * kScratchStride + k]
+                         : (coord == j - 1 ? scratch[(kPtsPerCta + pt) * kScratchStride + k] : 0.0f);
+            }
+          }
+          const uint32_t o = xoff(col, k);
+          store_split(s_pehi + o, s_pelo + o, v * kActScale);
+        }
+      } else {
+        if (t < kTileN) {
+          const long long gp = p0 + t;
+          float* pe = scratch + t * kScratchStride;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float vc = gp < n_pts ? __ldg(a.view + gp * 3 + c) : 0.0f;
+            pe[c] = vc;
+            float f = 1.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float sn, cs;
+              sincosf(vc * f, &sn, &cs);
+              pe[3 + 6 * i + c] = sn;
+              pe[6 + 6 * i + c] = cs;
+              f *= 2.0f;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        const int kpad = a.L[0].k_chunks * kChunkK;
+        const int F = a.feat_size;
+        for (int cidx = t; cidx < kTileN * kpad; cidx += kEpiThreads) {
+          const int col = cidx / kpad, k = cidx - col * kpad;
+          const long long gp = p0 + col;
+          float v = 0.0f;
+          if (gp < n_pts) {
+            if (k < 3) v = __ldg(a.x + gp * 3 + k);
+            else if (k < 30) v = scratch[col * kScratchStride + (k - 3)];
+            else if (k < 33) v = __ldg(a.normals + gp * 3 + (k - 30));
+            else if (k < 33 + F) v = __ldg(a.feats + gp * a.feat_stride + (k - 33));
+          }
+          const uint32_t o = xoff(col, k);
+          store_split(s_xhi + o, s_xlo + o, v * kActScale);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_all();
+      __syncwarp();
+      if (lane == 0) {                 // the whole first-layer operand is ready: both K halves
+        ptx::mbar_arrive_cluster(remote_x);
+        ptx::mbar_arrive_cluster(remote_x + 8);
+      }
+
+      // ---------------- layers
+      for (int l = 0; l < a.n_run; ++l) {
+        const LayerPlan& lp = a.L[l];
+        const bool last = (l == a.n_run - 1);
+        const int n_pair_tiles = (lp.m_tiles + 1) >> 1;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool skip_src = KIND == NET_SDF && l == a.skip_layer - 1;
+        float bias_r[kP2Tiles];
+#pragma unroll
+        for (int mp = 0; mp < kP2Tiles; ++mp) {
+          const int m = 2 * mp + (int)crank;
+          bias_r[mp] = m < lp.m_tiles ? __ldg(a.bias + lp.bias_off + m * kTileM + row) : 0.f;
+        }
+#pragma unroll
+        for (int mp = 0; mp < kP2Tiles; ++mp) {
+          if (mp < n_pair_tiles) {
+            ptx::mbar_wait(bar_acc + 8 * mp, acc_ctr[mp] & 1);
+            ++acc_ctr[mp];
+            ptx::tc_fence_after();
+            const int m = 2 * mp + (int)crank;
+            const int f = m * kTileM + row;                 // feature (output row) this thread owns
+            const bool have = m < lp.m_tiles;
+            const float bias = bias_r[mp];
+            // drain my 16 own + 16 peer columns of both accumulators; columns 0-63 of the pair tile are CTA 0's
+            uint32_t va[2][16], vb[2][16];
+#pragma unroll
+            for (int hcol = 0; hcol < 2; ++hcol) {
+              const uint32_t dest_h = hcol == 0 ? crank : (crank ^ 1u);
+              const uint32_t tcol = (uint32_t)(mp * 2 * kP2Cols) + dest_h * kTileN + (uint32_t)lcol0;
+              ptx::tmem_ld_32x16(t_row + tcol, va[hcol]);
+              ptx::tmem_ld_32x16(t_row + tcol + kP2Cols, vb[hcol]);
+            }
+            ptx::tmem_ld_wait();
+            if (mp == 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(remote_d1);
+            }
+            const bool write = have && !(skip_src && f >= a.skip_rows_begin);
+            const uint32_t o0 = xoff(lcol0, f);
+#pragma unroll
+            for (int hcol = 0; hcol < 2; ++hcol) {
+              const uint32_t dest_h = hcol == 0 ? crank : (crank ^ 1u);
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[hcol][j]) + __uint_as_float(vb[hcol][j]);
+              if (!last) {
+                uint32_t phi[8], plo[8];
+                if (MODE == 0) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float z0 = fmaf(v[2 * i], kInvScale, bias);
+                    const float z1 = fmaf(v[2 * i + 1], kInvScale, bias);
+                    const float y0 = (KIND == NET_SDF) ? softplus100_scaled(z0) : fmaxf(z0, 0.0f) * kActScale;
+                    const float y1 = (KIND == NET_SDF) ? softplus100_scaled(z1) : fmaxf(z1, 0.0f) * kActScale;
+                    pack_split(y0, y1, phi[i], plo[i]);
+                  }
+                } else {
+#pragma unroll
+                  for (int gq = 0; gq < 4; ++gq) {
+                    const float z = fmaf(v[4 * gq], kInvScale, bias);
+                    float sg;
+                    const float y = softplus100_scaled_grad(z, sg);
+                    const float ts = sg * (kInvScale * kActScale);
+                    pack_split(y, v[4 * gq + 1] * ts, phi[2 * gq], plo[2 * gq]);
+                    pack_split(v[4 * gq + 2] * ts, v[4 * gq + 3] * ts, phi[2 * gq + 1], plo[2 * gq + 1]);
+                  }
+                }
+                // every UMMA that reads X[mp] of the CURRENT layer retired before D_mp was committed: write in place
+                if (write) {
+                  if (hcol == 0) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
+                      ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      ptx::st_cluster_v4(dst_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
+                      ptx::st_cluster_v4(dst_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
+                    }
+                  }
+                }
+              } else if (have) {
+                // ---------------- head: write results to global memory
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int ccta = (int)dest_h, lc = lcol0 + j;   // owner CTA of the column and its index there
+                  const float acc = v[j] * kInvScale;
+                  if (KIND == NET_RENDER) {
+                    const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;
+                    if (row < 3 && m == 0 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
+                  } else {
+                    const long long gp = p0_pair + (long long)ccta * kPtsPerCta + ((MODE == 0) ? lc : (lc >> 2));
+                    const int jj = (MODE == 0) ? 0 : (lc & 3);
+                    if (gp < n_pts) {
+                      if (a.head == HEAD_SDF_ONLY) {
+                        if (f == 0) {
+                          if (jj == 0) a.out_sdf[gp] = acc + bias;
+                          else a.out_grad[gp * 3 + jj - 1] = acc;
+                        }
+                      } else {
+                        const int F = a.feat_size;
+                        if (jj == 0) {
+                          if (f < F) a.out_full[gp * (F + 2) + 2 + f] = acc + bias;
+                          else if (f < F + 2) {
+                            a.out_full[gp * (F + 2) + (f - F)] = acc + bias;
+                            if (f == F && a.out_sdf) a.out_sdf[gp] = acc + bias;
+                          }
+                        } else if (f == F) {
+                          a.out_grad[gp * 3 + jj - 1] = acc;
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+            }
+            if (!last) {
+              if (skip_src && mp == n_pair_tiles - 1) {
+                // skip connection: features [skip_rows_begin, +pe_dim) of MY 64 columns are the positional encoding
+                // (already scaled and split in my PE tile) -- each CTA fills them for its own columns
+                for (int cidx = t; cidx < a.pe_dim * 16; cidx += kEpiThreads) {
+                  const int k = cidx >> 4, blk = cidx & 15;           // 16 column blocks of 16 bytes per feature: 8 hi + 8 lo
+                  const int kd = a.skip_rows_begin + k;
+                  const uint4 pv = ptx::ld_shared_v4(s_pehi + (uint32_t)((k >> 3) * kBCoreStride + (k & 7) * 16 + blk * 128));
+                  ptx::st_shared_v4(s_xhi + (uint32_t)((kd >> 3) * kBCoreStride + (kd & 7) * 16 + blk * 128), pv.x, pv.y, pv.z, pv.w);
+                }
+              }
+              // X'[mp] (my rows, both CTAs' columns) is written: publish to the async proxy and tell the issuer
+              ptx::tc_fence_before();
+              ptx::fence_proxy_async_all();
+              __syncwarp();
+              if (lane == 0) {
+                ptx::mbar_arrive_cluster(remote_x + 8 * mp);
+                if (n_pair_tiles == 1) ptx::mbar_arrive_cluster(remote_x + 8);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();      // no CTA may exit (or free TMEM) while its peer can still write into it
+  if (warp == kEpiWarps + 1) ptx::tmem_dealloc_2cta(tmem_base, kTmemCols);
+}
+
+}  // namespace mvsdf
