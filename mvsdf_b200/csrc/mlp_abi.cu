@@ -228,7 +228,7 @@ static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, b
   const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : 0));
   ProfEvent* pe = prof_begin(kind, st);
   note_launch();
-  kern<<<2 * n_pairs, kMlpThreads, smem, st>>>(a);
+  kern<<<2 * n_pairs, VER == 2 ? kP2Threads : kMlpThreads, smem, st>>>(a);
   prof_end(pe, st);
   return check_cuda(cudaGetLastError(), "launch mlp_pair_kernel");
 }

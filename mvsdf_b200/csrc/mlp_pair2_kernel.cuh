@@ -8,8 +8,13 @@
 // UMMA order per layer:   (mp0,X0) (mp1,X0) (mp0,X1) | commit D_0 | (mp1,X1) | commit D_1
 //   * E_0 starts after 3/4 of the layer's UMMAs, and X[0] has been fully consumed by then, so E_0 overwrites
 //     X[0] in place as it goes (no register parking);
-//   * the next layer's (mp0,X'0) (mp1,X'0) only need E_0 (barrier bar_x0) and "D_1 drained to registers" (bar_d1);
-//     they run while E_1 produces X'[1] (barrier bar_x1).
+//   * the next layer's (mp0,X'0) (mp1,X'0) only need E_0 and "D_1 drained to registers" (bar_d1);
+//     they run while E_1 produces X'[1];
+//   * the half of every output tile that belongs to the peer's columns travels as st.async (STAS) with
+//     complete_tx on a barrier in the DESTINATION CTA (bar_lx[h], which also counts the 16 local epilogue warps),
+//     so no epilogue warp ever waits for a DSMEM round trip (measured: fence.proxy.async + release.cluster
+//     arrives after st.shared::cluster cost ~30 % of the epilogue warps' time).  CTA 1's warp 18 forwards
+//     "bar_lx[h] complete" to the issuer in CTA 0 (bar_px[h]).
 // Numerics, packed weights and epilogue math are those of mlp_kernel.cuh.
 #pragma once
 #include "mlp_kernel.cuh"
@@ -19,6 +24,7 @@ namespace mvsdf {
 constexpr int kP2Tiles = 2;                 // 256-row pair tiles per layer (width <= 512)
 constexpr int kP2Cols = 2 * kTileN;         // 128 columns per pair tile
 constexpr int kP2SplitChunks = 256 / kChunkK;   // K chunks that belong to X[0]
+constexpr int kP2Threads = kMlpThreads + 32;    // + the X-ready relay warp (used in CTA 1)
 
 // part p of a layer: 0 = (mp0, X0), 1 = (mp1, X0), 2 = (mp0, X1), 3 = (mp1, X1)
 __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, int& k0, int& k1, bool& run) {
@@ -31,7 +37,7 @@ __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, 
 }
 
 template <int KIND, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_pair2_kernel(const MlpArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_pair2_kernel(const MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -47,8 +53,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
   const uint32_t bar_full2 = s_bar + 8 * kStages;         // kStages: (leader only) the peer's half has landed
   const uint32_t bar_empty = s_bar + 16 * kStages;        // kStages: the UMMAs reading the stage retired (both CTAs)
   const uint32_t bar_acc = s_bar + 24 * kStages;          // kP2Tiles: accumulators of pair tile mp complete (both CTAs)
-  const uint32_t bar_x = bar_acc + 8 * kP2Tiles;          // 2 (leader only): B operand half h written in BOTH CTAs
-  const uint32_t bar_d1 = bar_x + 16;                     // (leader only) accumulator 1 drained to registers in BOTH CTAs
+  const uint32_t bar_lx = bar_acc + 8 * kP2Tiles;         // 2: half h of MY B operand is complete: 16 local warps + the peer's st.async bytes
+  const uint32_t bar_px = bar_lx + 16;                    // 2 (leader only): the peer's bar_lx[h] completed
+  const uint32_t bar_d1 = bar_px + 16;                    // (leader only) accumulator 1 drained to registers in BOTH CTAs
   const uint32_t s_tmem = bar_d1 + 8;
   uint8_t* const g_scratch = (KIND == NET_SDF) ? (smem + kStages * kStageBytes) : (smem + kStages * kStageBytes + xbytes);
   float* const scratch = reinterpret_cast<float*>(g_scratch);
@@ -67,8 +74,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
     for (int m = 0; m < kP2Tiles; ++m) ptx::mbar_init(bar_acc + 8 * m, 1);
-    ptx::mbar_init(bar_x, 2 * kEpiWarps);
-    ptx::mbar_init(bar_x + 8, 2 * kEpiWarps);
+    ptx::mbar_init(bar_lx, kEpiWarps);
+    ptx::mbar_init(bar_lx + 8, kEpiWarps);
+    ptx::mbar_init(bar_px, 1);
+    ptx::mbar_init(bar_px + 8, 1);
     ptx::mbar_init(bar_d1, 2 * kEpiWarps);
     ptx::fence_mbar_init();
   }
@@ -126,11 +135,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             int mp, k0, k1;
             bool run;
             p2_part(lp, part, mp, k0, k1, run);
-            if (part == 0) {          // X[0] of this layer written by both CTAs (also: D_0 drained by the previous E_0)
-              ptx::mbar_wait_cluster(bar_x, x_ctr & 1);
+            if (part == 0) {          // X[0] of this layer complete in both CTAs (also: D_0 drained by the previous E_0)
+              ptx::mbar_wait(bar_lx, x_ctr & 1);
+              ptx::mbar_wait_cluster(bar_px, x_ctr & 1);
+              ptx::fence_proxy_async_smem();     // observer-side fence for the bytes the peer delivered with st.async
               ptx::tc_fence_after();
-            } else if (part == 2) {   // X[1] written
-              ptx::mbar_wait_cluster(bar_x + 8, x_ctr & 1);
+            } else if (part == 2) {   // X[1] complete
+              ptx::mbar_wait(bar_lx + 8, x_ctr & 1);
+              ptx::mbar_wait_cluster(bar_px + 8, x_ctr & 1);
+              ptx::fence_proxy_async_smem();
               ptx::tc_fence_after();
               ++x_ctr;
             }
@@ -192,6 +205,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         }
       }
     }
+  } else if (warp == kEpiWarps + 2) {
+    if (crank == 1) {
+      // ------------------------------------------------------------------ X-ready relay: my bar_lx[h] -> the issuer's bar_px[h]
+      const uint32_t remote_px = ptx::mapa(bar_px, 0);
+      uint32_t x_ctr = 0;
+      for (long long g = pair0; g < n_tiles; g += pair_stride) {
+        for (int l = 0; l < a.n_run; ++l) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(bar_lx + 8 * h, x_ctr & 1);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(remote_px + 8 * h);
+            __syncwarp();
+          }
+          ++x_ctr;
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ prologue + epilogue warps
     const int q = warp & 3;              // TMEM lane quarter
@@ -202,7 +234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
     const int lcol0 = cg * 16;           // first column inside the destination CTA's 64
     const uint32_t dst_xhi = ptx::mapa(s_xhi, crank ^ 1u);   // the peer's activation buffer in the cluster window
     const uint32_t dst_xlo = dst_xhi + kBLoOffset;
-    const uint32_t remote_x = ptx::mapa(bar_x, 0);
+    const uint32_t dst_lx = ptx::mapa(bar_lx, crank ^ 1u);   // the barrier that counts the bytes I send to the peer
     const uint32_t remote_d1 = ptx::mapa(bar_d1, 0);
     constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
     uint32_t acc_ctr[kP2Tiles] = {0, 0};
@@ -289,11 +321,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
         }
       }
       ptx::tc_fence_before();
-      ptx::fence_proxy_async_all();
+      ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {                 // the whole first-layer operand is ready: both K halves
-        ptx::mbar_arrive_cluster(remote_x);
-        ptx::mbar_arrive_cluster(remote_x + 8);
+      if (lane == 0) {                 // the whole first-layer operand (my columns, local writes only) is ready: both K halves
+        ptx::mbar_arrive(bar_lx);
+        ptx::mbar_arrive(bar_lx + 8);
       }
 
       // ---------------- layers
@@ -323,7 +355,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             uint32_t va[2][16], vb[2][16];
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {
-              const uint32_t dest_h = hcol == 0 ? crank : (crank ^ 1u);
+              const uint32_t dest_h = hcol == 0 ? (crank ^ 1u) : crank;     // peer columns first: their st.async overlaps my own half
               const uint32_t tcol = (uint32_t)(mp * 2 * kP2Cols) + dest_h * kTileN + (uint32_t)lcol0;
               ptx::tmem_ld_32x16(t_row + tcol, va[hcol]);
               ptx::tmem_ld_32x16(t_row + tcol + kP2Cols, vb[hcol]);
@@ -332,13 +364,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
             if (mp == 1) {
               ptx::tc_fence_before();
               __syncwarp();
-              if (lane == 0) ptx::mbar_arrive_cluster(remote_d1);
+              if (lane == 0) ptx::mbar_arrive_remote_relaxed(remote_d1);
             }
             const bool write = have && !(skip_src && f >= a.skip_rows_begin);
             const uint32_t o0 = xoff(lcol0, f);
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {
-              const uint32_t dest_h = hcol == 0 ? crank : (crank ^ 1u);
+              const uint32_t dest_h = hcol == 0 ? (crank ^ 1u) : crank;     // peer columns first: their st.async overlaps my own half
               float v[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[hcol][j]) + __uint_as_float(vb[hcol][j]);
@@ -366,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                 }
                 // every UMMA that reads X[mp] of the CURRENT layer retired before D_mp was committed: write in place
                 if (write) {
-                  if (hcol == 0) {
+                  if (hcol == 1) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
@@ -375,8 +407,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                   } else {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                      ptx::st_cluster_v4(dst_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
-                      ptx::st_cluster_v4(dst_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
+                      ptx::st_async_v4(dst_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3], dst_lx + 8 * mp);
+                      ptx::st_async_v4(dst_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3], dst_lx + 8 * mp);
                     }
                   }
                 }
@@ -426,13 +458,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1) mlp_
                   ptx::st_shared_v4(s_xhi + (uint32_t)((kd >> 3) * kBCoreStride + (kd & 7) * 16 + blk * 128), pv.x, pv.y, pv.z, pv.w);
                 }
               }
-              // X'[mp] (my rows, both CTAs' columns) is written: publish to the async proxy and tell the issuer
+              // my rows of X'[mp] for my own columns are written (the peer's rows arrive as st.async bytes on the
+              // same barrier): publish to the async proxy and arrive; warp 0 also arms the expected byte count
               ptx::tc_fence_before();
-              ptx::fence_proxy_async_all();
+              ptx::fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                ptx::mbar_arrive_cluster(remote_x + 8 * mp);
-                if (n_pair_tiles == 1) ptx::mbar_arrive_cluster(remote_x + 8);
+                if (warp == 0) {
+                  const int pm = 2 * mp + (int)(crank ^ 1u);       // the peer's output tile: 256 B per row it writes
+                  int rows = pm < lp.m_tiles ? kTileM : 0;
+                  if (skip_src) rows = min(rows, max(a.skip_rows_begin - pm * kTileM, 0));
+                  if (rows > 0) ptx::mbar_arrive_expect_tx(bar_lx + 8 * mp, (uint32_t)rows * (kTileN * 4));
+                  else ptx::mbar_arrive(bar_lx + 8 * mp);
+                } else {
+                  ptx::mbar_arrive(bar_lx + 8 * mp);
+                }
+                if (n_pair_tiles == 1) ptx::mbar_arrive(bar_lx + 8);
               }
             }
           }
