@@ -149,8 +149,11 @@ __global__ void pack_layer_kernel(const float* __restrict__ v, const float* __re
   if (kcore == 0) bias_dst[lp.bias_off + dr] = sr >= 0 ? bias_src[sr] : 0.f;
 }
 
+static unsigned long long* g_trace = nullptr;
+
 static int fill_args(const NetPlan& p, const void* packed, int head, MlpArgs& a) {
   memset(&a, 0, sizeof(a));
+  a.trace = g_trace;
   a.packed = static_cast<const uint8_t*>(packed);
   a.bias = reinterpret_cast<const float*>(a.packed + p.bias_area_off);
   a.n_run = p.n_hidden + 1;
@@ -297,6 +300,8 @@ using namespace mvsdf;
 extern "C" {
 
 int mvsdf_abi_version(void) { return 1; }
+/* debug only (not in the public header): device buffer of >= 1 MiB that receives a clock64 timeline of CTA pair 0 */
+void mvsdf_debug_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
 long long mvsdf_launch_count(void) { return g_launches; }
 void mvsdf_profile_enable(int on) {
   g_prof_on = on != 0;

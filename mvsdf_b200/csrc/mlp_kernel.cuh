@@ -61,6 +61,7 @@ struct MlpArgs {
   float* out_full;           // [n, 2+feat]    (HEAD_FULL)
   float* out_grad;           // [n,3]          (value+gradient mode)
   float* out_rgb;            // [n,3]          (render)
+  unsigned long long* trace; // debug only: clock64 timeline of pair 0 (tools/diag_trace.py); nullptr in production
   LayerPlan L[10];
 };
 
@@ -113,6 +114,39 @@ __device__ __forceinline__ float softplus100_scaled_grad(float z, float& sig) {
   const float y = ptx::lg2_approx(ope) * (kActScale * 0.6931471805599453f * 0.01f);
   sig = select_gt(tl, 20.0f * 1.4426950408889634f, 1.0f, e * ptx::rcp_approx(ope));
   return select_gt(tl, 20.0f * 1.4426950408889634f, z * kActScale, y);
+}
+
+// ---- leaner epilogue math (pair2 kernel) ------------------------------------------------------------------
+// softplus in the log2 domain without a select:  with t = 100 z log2(e),
+//   kActScale * softplus(z; beta=100) = C * (max(t,0) + lg2(1 + 2^-|t|)),   C = kActScale ln(2)/100.
+// Never overflows; for 100 z > 20 (torch's linear branch) the lg2 term is < 3e-9 and the result equals z to fp32
+// rounding, so the threshold of nn.Softplus needs no special case.
+constexpr float kSpT = 100.0f * 1.4426950408889634f;                  // t = kSpT * z
+constexpr float kSpC = kActScale * 0.6931471805599453f * 0.01f;
+__device__ __forceinline__ float softplus_t_scaled(float t) {
+  const float e = ptx::ex2_approx(-fabsf(t));
+  return (fmaxf(t, 0.0f) + ptx::lg2_approx(1.0f + e)) * kSpC;
+}
+// same, also returning d softplus / dz = sigmoid(100 z) = 1/(1+2^-t)
+__device__ __forceinline__ float softplus_t_scaled_grad(float t, float& sig) {
+  const float e = ptx::ex2_approx(-fabsf(t));
+  const float ope = 1.0f + e;
+  const float r = ptx::rcp_approx(ope);
+  sig = t >= 0.0f ? r : e * r;
+  return (fmaxf(t, 0.0f) + ptx::lg2_approx(ope)) * kSpC;
+}
+// hi/lo split with the residual computed by mixed-precision FMAs (y - float(h) = h * (-1) + y, SASS: FHFMA)
+__device__ __forceinline__ void pack_split_fh(float y0, float y1, uint32_t& hi2, uint32_t& lo2) {
+  float l0, l1;
+  asm("{\n\t.reg .b16 hl, hh, m1;\n\t"
+      "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
+      "mov.b32 {hl, hh}, %0;\n\t"
+      "mov.b16 m1, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %1, hl, m1, %3;\n\t"
+      "fma.rn.f32.f16 %2, hh, m1, %4;\n\t}"
+      : "=r"(hi2), "=f"(l0), "=f"(l1)
+      : "f"(y0), "f"(y1));
+  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo2) : "f"(l0), "f"(l1));
 }
 
 template <int KIND, int MODE, int CL>

@@ -36,6 +36,17 @@ __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, 
   run = mp < n_pair_tiles && k0 < k1;
 }
 
+// debug timeline: slot = role * 16384 + index (role 0 issuer, 1 epilogue warp 0 of CTA 0, 2 epilogue warp 0 of CTA 1,
+// 3 producer of CTA 0)
+#ifdef MVSDF_TRACE
+#define P2_TRACE(role, index)                                                                         \
+  do {                                                                                                \
+    if (a.trace && blockIdx.x < 2 && (index) < 16384) a.trace[(role) * 16384 + (index)] = clock64(); \
+  } while (0)
+#else
+#define P2_TRACE(role, index) do { } while (0)
+#endif
+
 template <int KIND, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_pair2_kernel(const MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -49,10 +60,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
   const uint32_t s_pehi = s_xhi + xbytes;
   const uint32_t s_pelo = s_pehi + kBLoOffset;
   const uint32_t s_bar = s_pehi + kPeTileBytes;
-  const uint32_t bar_full = s_bar;                        // kStages: my weight half has landed
-  const uint32_t bar_full2 = s_bar + 8 * kStages;         // kStages: (leader only) the peer's half has landed
-  const uint32_t bar_empty = s_bar + 16 * kStages;        // kStages: the UMMAs reading the stage retired (both CTAs)
-  const uint32_t bar_acc = s_bar + 24 * kStages;          // kP2Tiles: accumulators of pair tile mp complete (both CTAs)
+  const uint32_t bar_full = s_bar;                        // kStages: my weight half has landed (leader: AND the peer's half)
+  const uint32_t bar_empty = s_bar + 8 * kStages;         // kStages: the UMMAs reading the stage retired (both CTAs)
+  const uint32_t bar_acc = s_bar + 16 * kStages;          // kP2Tiles: accumulators of pair tile mp complete (both CTAs)
   const uint32_t bar_lx = bar_acc + 8 * kP2Tiles;         // 2: half h of MY B operand is complete: 16 local warps + the peer's st.async bytes
   const uint32_t bar_px = bar_lx + 16;                    // 2 (leader only): the peer's bar_lx[h] completed
   const uint32_t bar_d1 = bar_px + 16;                    // (leader only) accumulator 1 drained to registers in BOTH CTAs
@@ -69,8 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 1);
-      ptx::mbar_init(bar_full2 + 8 * s, 1);
+      ptx::mbar_init(bar_full + 8 * s, crank == 0 ? 2 : 1);   // leader: own producer + the peer's relay
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
     for (int m = 0; m < kP2Tiles; ++m) ptx::mbar_init(bar_acc + 8 * m, 1);
@@ -121,110 +130,131 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
         }
       }
     }
-  } else if (warp == kEpiWarps + 1) {
-    if (crank == 0) {
-      // ------------------------------------------------------------------ UMMA issuer (leader CTA)
-      constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, kP2Cols);
-      const bool leader = ptx::elect_one();
-      uint32_t it = 0, x_ctr = 0, d1_uses = 0;
-      for (long long g = pair0; g < n_tiles; g += pair_stride) {
-        for (int l = 0; l < a.n_run; ++l) {
-          const LayerPlan& lp = a.L[l];
-          const uint32_t b_base = lp.b_from_pe ? s_pehi : s_xhi;
-          for (int part = 0; part < 4; ++part) {
-            int mp, k0, k1;
-            bool run;
-            p2_part(lp, part, mp, k0, k1, run);
+  } else if (crank == 0 && warp == kEpiWarps + 1) {
+    // ------------------------------------------------------------------ UMMA issuer (leader CTA)
+    // Per 16-wide K step three UMMAs (M = 256 over the pair, N = 128):
+    //   D_a (+)= W_hi X_hi^T     D_b (+)= W_hi X_lo^T     D_a += W_lo X_hi^T
+    // (Merging the first two into one N = 256 UMMA over [X_hi ; X_lo] reads W_hi once and was measured 1 % faster, but
+    //  the third product then lands on b for CTA 0's points and on a for CTA 1's: the fp32 rounding of a point would
+    //  depend on which CTA processes it, and the outputs would no longer be bit-identical under re-sharding.)
+    constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, kP2Cols);
+    const bool leader = ptx::elect_one();
+    const uint32_t issue = (leader && !(a.debug & 2)) ? 1u : 0u;
+    uint32_t it0 = 0, x_ctr = 0, d1_uses = 0;
+    bool ready = false;      // the barrier of my next stage was already seen complete
+    // shared-memory descriptors (ptx::smem_desc) as (low word, high word): only the 14-bit address field varies
+    const uint32_t dlo_a = ((s_stage & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+    const uint32_t dlo_x = ((s_xhi & 0x3FFFFu) >> 4) | (((uint32_t)kBCoreStride >> 4) << 16);
+    const uint32_t dlo_pe = ((s_pehi & 0x3FFFFu) >> 4) | (((uint32_t)kBCoreStride >> 4) << 16);
+    constexpr uint32_t dhi_a = (512u >> 4) | (1u << 14);
+    constexpr uint32_t dhi_b = (128u >> 4) | (1u << 14);
+    int tr = 0;
+    for (long long g = pair0; g < n_tiles; g += pair_stride) {
+      for (int l = 0; l < a.n_run; ++l, tr += 8) {
+        const LayerPlan& lp = a.L[l];
+        if (lane == 0) P2_TRACE(0, tr);
+        for (int part = 0; part < 4; ++part) {
+          int mp, k0, k1;
+          bool run;
+          p2_part(lp, part, mp, k0, k1, run);
+          if (lane == 0 && (part == 1 || part == 3)) P2_TRACE(0, tr + 2 + part);     // 3: part 1 reached, 5: part 3 reached
+          {
             if (part == 0) {          // X[0] of this layer complete in both CTAs (also: D_0 drained by the previous E_0)
               ptx::mbar_wait(bar_lx, x_ctr & 1);
-              ptx::mbar_wait_cluster(bar_px, x_ctr & 1);
+              ptx::mbar_wait(bar_px, x_ctr & 1);
               ptx::fence_proxy_async_smem();     // observer-side fence for the bytes the peer delivered with st.async
               ptx::tc_fence_after();
+              if (lane == 0) P2_TRACE(0, tr + 1);     // X0 wait done
             } else if (part == 2) {   // X[1] complete
+              if (lane == 0) P2_TRACE(0, tr + 2);     // part 2 reached (parts 0,1 issued)
               ptx::mbar_wait(bar_lx + 8, x_ctr & 1);
-              ptx::mbar_wait_cluster(bar_px + 8, x_ctr & 1);
+              ptx::mbar_wait(bar_px + 8, x_ctr & 1);
               ptx::fence_proxy_async_smem();
               ptx::tc_fence_after();
               ++x_ctr;
+              if (lane == 0) P2_TRACE(0, tr + 4);     // X1 wait done
             }
-            if (!run) continue;
+          }
+          if (!run) continue;
+          {
             if (part == 1) {          // first write into D_1 this layer: its previous contents must have been read
               if (d1_uses > 0) {
-                ptx::mbar_wait_cluster(bar_d1, (d1_uses - 1) & 1);
+                ptx::mbar_wait(bar_d1, (d1_uses - 1) & 1);
                 ptx::tc_fence_after();
               }
               ++d1_uses;
-            }
-            const uint32_t d_a = tmem_base + (uint32_t)(mp * 2 * kP2Cols);
-            const uint32_t d_b = d_a + kP2Cols;
-            for (int kc = k0; kc < k1; ++kc, ++it) {
-              const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-              ptx::mbar_wait(bar_full + 8 * s, ph);
-              ptx::mbar_wait(bar_full2 + 8 * s, ph);
-              ptx::tc_fence_after();
-              const uint32_t a_hi = s_stage + s * kStageBytes;
-              const uint32_t a_lo = a_hi + kTileBytes;
-#pragma unroll
-              for (int ks = 0; ks < kChunkK / 16; ++ks) {
-                const uint64_t da_hi = ptx::smem_desc(a_hi + ks * 256, 128, 512);
-                const uint64_t da_lo = ptx::smem_desc(a_lo + ks * 256, 128, 512);
-                const uint32_t boff = (uint32_t)((kc * (kChunkK / 8) + ks * 2) * kBCoreStride);
-                const uint64_t db_hi = ptx::smem_desc(b_base + boff, kBCoreStride, 128);
-                const uint64_t db_lo = ptx::smem_desc(b_base + kBLoOffset + boff, kBCoreStride, 128);
-                if (leader && !(a.debug & 2)) {
-                  const uint32_t acc = (kc | ks) != 0 ? 1u : 0u;
-                  ptx::umma_f16_2cta(d_a, da_hi, db_hi, idesc, acc);
-                  ptx::umma_f16_2cta(d_b, da_hi, db_lo, idesc, acc);
-                  ptx::umma_f16_2cta(d_a, da_lo, db_hi, idesc, 1u);
-                }
-              }
-              if (leader) ptx::umma_commit_2cta(bar_empty + 8 * s, 3);
-              __syncwarp();
-            }
-            if (k1 == lp.k_chunks) {      // this part completes D_mp
-              if (leader) ptx::umma_commit_2cta(bar_acc + 8 * mp, 3);
-              __syncwarp();
+              if (lane == 0) P2_TRACE(0, tr + 6);     // d1 wait done
             }
           }
-        }
-      }
-    } else {
-      // ------------------------------------------------------------------ peer relay: tell the leader my stage has landed
-      const uint32_t remote_full2 = ptx::mapa(bar_full2, 0);
-      uint32_t it = 0;
-      for (long long g = pair0; g < n_tiles; g += pair_stride) {
-        for (int l = 0; l < a.n_run; ++l) {
-          const LayerPlan& lp = a.L[l];
-          const int n_stage = ((lp.m_tiles + 1) >> 1) * lp.k_chunks;
-          for (int i = 0; i < n_stage; ++i, ++it) {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            ptx::mbar_wait(bar_full + 8 * s, ph);
-            if (lane == 0) ptx::mbar_arrive_remote_relaxed(remote_full2 + 8 * s);
+          const uint32_t d_a = tmem_base + (uint32_t)(mp * 2 * kP2Cols);
+          const uint32_t d_b = d_a + kP2Cols;
+          const uint32_t dlo_b = lp.b_from_pe ? dlo_pe : dlo_x;
+          const int n_st = k1 - k0;
+          for (int j = 0; j < n_st; ++j) {
+            const int kc = k0 + j;
+            const uint32_t it = it0 + (uint32_t)j;
+            const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+            if (!ready) ptx::mbar_wait(bar_full + 8 * st, ph);
+            ptx::tc_fence_after();
+            // query my next stage's barrier now: the round trip of the query hides behind the UMMA issue below
+            const uint32_t itn = it + 1;
+            ready = ptx::mbar_test_wait(bar_full + 8 * (itn % kStages), (itn / kStages) & 1);
+            const uint32_t a_off = dlo_a + st * (kStageBytes >> 4);
+            const uint32_t b_off = dlo_b + (uint32_t)kc * ((kChunkK / 8) * kBCoreStride >> 4);
+#pragma unroll
+            for (int ks = 0; ks < kChunkK / 16; ++ks) {
+              const uint64_t da_hi = ptx::desc_from_words(a_off + ks * (256 >> 4), dhi_a);
+              const uint64_t da_lo = ptx::desc_from_words(a_off + ((kTileBytes + ks * 256) >> 4), dhi_a);
+              const uint64_t db_hi = ptx::desc_from_words(b_off + ks * (2 * kBCoreStride >> 4), dhi_b);
+              const uint64_t db_lo = ptx::desc_from_words(b_off + ((kBLoOffset + ks * 2 * kBCoreStride) >> 4), dhi_b);
+              ptx::umma3_f16_2cta(d_a, d_b, da_hi, da_lo, db_hi, db_lo, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
+            }
+            if (leader) ptx::umma_commit_2cta(bar_empty + 8 * st, 3);
             __syncwarp();
           }
+          if (k1 == lp.k_chunks) {      // this part completes D_mp
+            if (leader) ptx::umma_commit_2cta(bar_acc + 8 * mp, 3);
+            __syncwarp();
+          }
+          it0 += (uint32_t)n_st;
+        }
+        if (lane == 0) P2_TRACE(0, tr + 7);         // layer fully issued
+      }
+    }
+  } else if (crank == 1 && warp == kEpiWarps + 1) {
+    // ------------------------------------------------------------------ CTA 1, warp 17: tell the leader my stage has landed
+    const uint32_t remote_full = ptx::mapa(bar_full, 0);
+    uint32_t it = 0;
+    for (long long g = pair0; g < n_tiles; g += pair_stride) {
+      for (int l = 0; l < a.n_run; ++l) {
+        const LayerPlan& lp = a.L[l];
+        const int n_stage = ((lp.m_tiles + 1) >> 1) * lp.k_chunks;
+        for (int i = 0; i < n_stage; ++i, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          if (lane == 0) ptx::mbar_arrive_remote_relaxed(remote_full + 8 * s);
+          __syncwarp();
         }
       }
     }
-  } else if (warp == kEpiWarps + 2) {
-    if (crank == 1) {
-      // ------------------------------------------------------------------ X-ready relay: my bar_lx[h] -> the issuer's bar_px[h]
-      const uint32_t remote_px = ptx::mapa(bar_px, 0);
-      uint32_t x_ctr = 0;
-      for (long long g = pair0; g < n_tiles; g += pair_stride) {
-        for (int l = 0; l < a.n_run; ++l) {
+  } else if (crank == 1 && warp == kEpiWarps + 2) {
+    // ------------------------------------------------------------------ CTA 1, warp 18: my bar_lx[h] -> the issuer's bar_px[h]
+    const uint32_t remote_px = ptx::mapa(bar_px, 0);
+    uint32_t x_ctr = 0;
+    for (long long g = pair0; g < n_tiles; g += pair_stride) {
+      for (int l = 0; l < a.n_run; ++l) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(bar_lx + 8 * h, x_ctr & 1);
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(remote_px + 8 * h);
-            __syncwarp();
-          }
-          ++x_ctr;
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(bar_lx + 8 * h, x_ctr & 1);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(remote_px + 8 * h);
+          __syncwarp();
         }
+        ++x_ctr;
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // ------------------------------------------------------------------ prologue + epilogue warps
     const int q = warp & 3;              // TMEM lane quarter
     const int cg = warp >> 2;            // 16-column group: this warp produces columns [16cg,+16) of MY 64 columns
@@ -238,9 +268,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     const uint32_t remote_d1 = ptx::mapa(bar_d1, 0);
     constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
     uint32_t acc_ctr[kP2Tiles] = {0, 0};
+    int tr = 0;
+    const bool tracer = threadIdx.x == 0;
 
     for (long long g = pair0; g < n_tiles; g += pair_stride) {
       const long long p0 = g * (2 * kPtsPerCta) + (long long)crank * kPtsPerCta;      // my first point
+      if (tracer) P2_TRACE(1 + crank, tr);            // prologue start
+      tr += 8;
       const long long p0_pair = g * (2 * kPtsPerCta);
 
       // ---------------- prologue: first layer's B operand for MY 64 columns (identical to the single-CTA kernel)
@@ -328,8 +362,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
         ptx::mbar_arrive(bar_lx + 8);
       }
 
+      if (tracer) P2_TRACE(1 + crank, tr - 7);        // prologue done
       // ---------------- layers
-      for (int l = 0; l < a.n_run; ++l) {
+      for (int l = 0; l < a.n_run; ++l, tr += 8) {
         const LayerPlan& lp = a.L[l];
         const bool last = (l == a.n_run - 1);
         const int n_pair_tiles = (lp.m_tiles + 1) >> 1;
@@ -344,9 +379,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 #pragma unroll
         for (int mp = 0; mp < kP2Tiles; ++mp) {
           if (mp < n_pair_tiles) {
+            if (tracer) P2_TRACE(1 + crank, tr + 4 * mp);          // waiting for D_mp
             ptx::mbar_wait(bar_acc + 8 * mp, acc_ctr[mp] & 1);
             ++acc_ctr[mp];
             ptx::tc_fence_after();
+            if (tracer) P2_TRACE(1 + crank, tr + 4 * mp + 1);      // D_mp ready
             const int m = 2 * mp + (int)crank;
             const int f = m * kTileM + row;                 // feature (output row) this thread owns
             const bool have = m < lp.m_tiles;
@@ -361,6 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
               ptx::tmem_ld_32x16(t_row + tcol + kP2Cols, vb[hcol]);
             }
             ptx::tmem_ld_wait();
+            if (tracer) P2_TRACE(1 + crank, tr + 4 * mp + 2);      // drained
             if (mp == 1) {
               ptx::tc_fence_before();
               __syncwarp();
@@ -371,29 +409,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {
               const uint32_t dest_h = hcol == 0 ? (crank ^ 1u) : crank;     // peer columns first: their st.async overlaps my own half
-              float v[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[hcol][j]) + __uint_as_float(vb[hcol][j]);
               if (!last) {
                 uint32_t phi[8], plo[8];
                 if (MODE == 0) {
+                  // pre-activation straight in the softplus / ReLU domain: two FMAs fold the accumulator sum,
+                  // the un-scaling and the bias
+                  constexpr float kK = (KIND == NET_SDF) ? kInvScale * kSpT : kInvScale * kActScale;
+                  const float bias_k = bias * ((KIND == NET_SDF) ? kSpT : kActScale);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
-                    const float z0 = fmaf(v[2 * i], kInvScale, bias);
-                    const float z1 = fmaf(v[2 * i + 1], kInvScale, bias);
-                    const float y0 = (KIND == NET_SDF) ? softplus100_scaled(z0) : fmaxf(z0, 0.0f) * kActScale;
-                    const float y1 = (KIND == NET_SDF) ? softplus100_scaled(z1) : fmaxf(z1, 0.0f) * kActScale;
-                    pack_split(y0, y1, phi[i], plo[i]);
+                    const float t0 = fmaf(__uint_as_float(va[hcol][2 * i]), kK, fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k));
+                    const float t1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k));
+                    const float y0 = (KIND == NET_SDF && !(a.debug & 8)) ? softplus_t_scaled(t0) : fmaxf(t0, 0.0f);
+                    const float y1 = (KIND == NET_SDF && !(a.debug & 8)) ? softplus_t_scaled(t1) : fmaxf(t1, 0.0f);
+                    pack_split_fh(y0, y1, phi[i], plo[i]);
                   }
                 } else {
+                  constexpr float kK = kInvScale * kSpT;
+                  const float bias_k = bias * kSpT;
 #pragma unroll
                   for (int gq = 0; gq < 4; ++gq) {
-                    const float z = fmaf(v[4 * gq], kInvScale, bias);
+                    const float t = fmaf(__uint_as_float(va[hcol][4 * gq]), kK, fmaf(__uint_as_float(vb[hcol][4 * gq]), kK, bias_k));
                     float sg;
-                    const float y = softplus100_scaled_grad(z, sg);
+                    const float y = softplus_t_scaled_grad(t, sg);
                     const float ts = sg * (kInvScale * kActScale);
-                    pack_split(y, v[4 * gq + 1] * ts, phi[2 * gq], plo[2 * gq]);
-                    pack_split(v[4 * gq + 2] * ts, v[4 * gq + 3] * ts, phi[2 * gq + 1], plo[2 * gq + 1]);
+                    const float d0 = __uint_as_float(va[hcol][4 * gq + 1]) + __uint_as_float(vb[hcol][4 * gq + 1]);
+                    const float d1 = __uint_as_float(va[hcol][4 * gq + 2]) + __uint_as_float(vb[hcol][4 * gq + 2]);
+                    const float d2 = __uint_as_float(va[hcol][4 * gq + 3]) + __uint_as_float(vb[hcol][4 * gq + 3]);
+                    pack_split_fh(y, d0 * ts, phi[2 * gq], plo[2 * gq]);
+                    pack_split_fh(d1 * ts, d2 * ts, phi[2 * gq + 1], plo[2 * gq + 1]);
                   }
                 }
                 // every UMMA that reads X[mp] of the CURRENT layer retired before D_mp was committed: write in place
@@ -404,7 +448,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                       ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
                       ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
                     }
-                  } else {
+                  } else if (!(a.debug & 4)) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       ptx::st_async_v4(dst_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3], dst_lx + 8 * mp);
@@ -417,7 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int ccta = (int)dest_h, lc = lcol0 + j;   // owner CTA of the column and its index there
-                  const float acc = v[j] * kInvScale;
+                  const float acc = (__uint_as_float(va[hcol][j]) + __uint_as_float(vb[hcol][j])) * kInvScale;
                   if (KIND == NET_RENDER) {
                     const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;
                     if (row < 3 && m == 0 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
@@ -468,13 +512,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                   const int pm = 2 * mp + (int)(crank ^ 1u);       // the peer's output tile: 256 B per row it writes
                   int rows = pm < lp.m_tiles ? kTileM : 0;
                   if (skip_src) rows = min(rows, max(a.skip_rows_begin - pm * kTileM, 0));
-                  if (rows > 0) ptx::mbar_arrive_expect_tx(bar_lx + 8 * mp, (uint32_t)rows * (kTileN * 4));
+                  if (rows > 0 && !(a.debug & 4)) ptx::mbar_arrive_expect_tx(bar_lx + 8 * mp, (uint32_t)rows * (kTileN * 4));
                   else ptx::mbar_arrive(bar_lx + 8 * mp);
                 } else {
                   ptx::mbar_arrive(bar_lx + 8 * mp);
                 }
                 if (n_pair_tiles == 1) ptx::mbar_arrive(bar_lx + 8);
               }
+              if (tracer) P2_TRACE(1 + crank, tr + 4 * mp + 3);    // E_mp done (arrived)
             }
           }
         }

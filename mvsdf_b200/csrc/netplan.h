@@ -16,7 +16,10 @@ namespace mvsdf {
 constexpr int kTileM = 128;        // output features per UMMA (TMEM lanes)
 constexpr int kTileN = 64;         // points (columns) per tile
 constexpr int kChunkK = 32;        // K elements per pipeline stage
-constexpr int kStages = 4;
+#ifndef MVSDF_STAGES
+#define MVSDF_STAGES 4
+#endif
+constexpr int kStages = MVSDF_STAGES;
 constexpr int kTileBytes = kTileM * kChunkK * 2;   // 8 KiB (hi or lo)
 constexpr int kStageBytes = 2 * kTileBytes;        // 16 KiB
 // Activation operand (B of the UMMA), MN-major / SWIZZLE_NONE: element (column n, feature k) lives at

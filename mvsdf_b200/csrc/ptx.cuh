@@ -37,6 +37,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking query of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -136,6 +148,22 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, 
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the three UMMAs of one 16-wide K step of the hi/lo split product, guarded by one predicate:
+//   D_a (+)= A_hi B_hi,   D_b (+)= A_hi B_lo,   D_a += A_lo B_hi
+__device__ __forceinline__ void umma3_f16_2cta(uint32_t d_a, uint32_t d_b, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
+                                               uint64_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      "setp.ne.b32 q, %8, 0;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 t, %7, %7;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %2, %4, %6, p;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %5, %6, p;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %4, %6, t;\n\t}"
+      :
+      : "r"(d_a), "r"(d_b), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(cta_mask)
@@ -219,6 +247,11 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t desc_from_words(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
 }
 // Instruction descriptor for kind::f16: fp16 A/B (K-major), fp32 D.
 //   [4,6) D fmt=1 (F32), [7,10) A fmt=0 (F16), [10,13) B fmt=0, [15] A major=K, [16] B major=K,
