@@ -126,6 +126,17 @@ int mvsdf_shade_rays(const mvsdf_net* sdf_net, const void* sdf_packed, const mvs
                      float* out_sdf, float* out_rgb_values, float* out_surf_pts, float* out_normals, float* out_surf_head,
                      int32_t* out_hit_index, int32_t* out_hit_offsets, void* stream);
 
+/* ---- depth-surface samples of training phase 0 (implicit_differentiable_renderer.py:226-239; helpers
+ * code/utils/my_utils.py:71-95 get_pixel_grids / idx_img2cam / idx_cam2world): back-projects every pixel of the MVS
+ * depth maps into the normalised object frame.
+ *   depths [n_maps,h,w]; k_inv [n_maps,3,3] = inverse(depth_cams[.,1,:3,:3]); e_inv [n_maps,4,4] = inverse(depth_cams[.,0])
+ *   (the caller inverts, as the reference does with torch.inverse); center [3], size [1];
+ *   out_pts [n_maps*h*w,3] = (x_world - center) / size * 2, out_valid [n_maps*h*w] uint8 = depth > 0.
+ * The boolean-mask compaction, the +-0.1 jitter and the np.random.choice sub-sampling (:240-247) take host-supplied
+ * randomness and stay on the host side (mvsdf_b200/network.py). */
+int mvsdf_depth_backproject(const float* depths, const float* k_inv, const float* e_inv, int n_maps, int h, int w,
+                            const float* center, const float* size, float* out_pts, uint8_t* out_valid, void* stream);
+
 /* ---- IDRLoss.get_feat_loss_corr (code/model/loss.py:115-165; helpers code/utils/my_utils.py:98-165) ---------
  * Feature maps are constants of the scene (scene_dataset.py:141-149): restack them once into channels-last with
  * mvsdf_feat_nchw_to_nhwc ([n,32,h,w] -> [n,h,w,32]) so that every bilinear tap is one 128-byte load.

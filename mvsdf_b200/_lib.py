@@ -60,6 +60,8 @@ def _declare(lib):
     lib.mvsdf_shade_workspace_bytes.argtypes = [c_int64, c_int]
     lib.mvsdf_shade_rays.restype = c_int
     lib.mvsdf_shade_rays.argtypes = [P, P, P, P, P, P, P, c_int, c_int, c_int, c_size_t, P, P, P, P, P, P, P, P, P]
+    lib.mvsdf_depth_backproject.restype = c_int
+    lib.mvsdf_depth_backproject.argtypes = [P, P, P, c_int, c_int, c_int, P, P, P, P, P]
     lib.mvsdf_feat_nchw_to_nhwc.restype = c_int
     lib.mvsdf_feat_nchw_to_nhwc.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
     lib.mvsdf_feat_loss_partials.restype = c_int

@@ -338,7 +338,68 @@ static ShadeLayout shade_layout(int64_t R, int feat) {
 
 using namespace mvsdf;
 
+// ------------------------------------------------------------------ depth-surface points (phase 0 of training)
+// One thread per depth pixel: get_pixel_grids -> idx_img2cam -> idx_cam2world (utils/my_utils.py:71-95) and the
+// normalisation (x - center) / size * 2 of implicit_differentiable_renderer.py:236-239.  The two matrix inverses are
+// supplied by the caller (torch.inverse of 3x3 / 4x4 blocks, like the reference); products are summed in index order
+// without FMA contraction, like the separate torch ops.
+__global__ void depth_backproject_kernel(const float* __restrict__ depths, const float* __restrict__ k_inv,
+                                         const float* __restrict__ e_inv, int n_maps, int h, int w,
+                                         const float* __restrict__ center, const float* __restrict__ size,
+                                         float* __restrict__ pts, uint8_t* __restrict__ valid) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_maps * h * w;
+  if (idx >= total) return;
+  const int x = (int)(idx % w);
+  const int y = (int)((idx / w) % h);
+  const int n = (int)(idx / ((long long)w * h));
+  const float d = depths[idx];
+  const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+  const float* Ki = k_inv + n * 9;
+  float c[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    c[r] = __fadd_rn(__fadd_rn(__fmul_rn(Ki[r * 3 + 0], px), __fmul_rn(Ki[r * 3 + 1], py)), Ki[r * 3 + 2]);
+  const float cz = __fadd_rn(c[2], 1e-9f);
+  float ch[4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) ch[r] = __fmul_rn(__fdiv_rn(c[r], cz), d);
+  ch[3] = 1.0f;
+  const float* Ei = e_inv + n * 16;
+  float wv[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float acc = __fmul_rn(Ei[r * 4 + 0], ch[0]);
+    acc = __fadd_rn(acc, __fmul_rn(Ei[r * 4 + 1], ch[1]));
+    acc = __fadd_rn(acc, __fmul_rn(Ei[r * 4 + 2], ch[2]));
+    acc = __fadd_rn(acc, __fmul_rn(Ei[r * 4 + 3], ch[3]));
+    wv[r] = acc;
+  }
+  const float ww = __fadd_rn(wv[3], 1e-9f);
+  const float sz = size[0];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float p = __fdiv_rn(wv[r], ww);
+    pts[idx * 3 + r] = __fmul_rn(__fdiv_rn(__fsub_rn(p, center[r]), sz), 2.0f);
+  }
+  valid[idx] = d > 0.0f ? 1 : 0;
+}
+
 extern "C" {
+
+int mvsdf_depth_backproject(const float* depths, const float* k_inv, const float* e_inv, int n_maps, int h, int w,
+                            const float* center, const float* size, float* out_pts, uint8_t* out_valid, void* stream) {
+  if (sm_count() <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
+  if (n_maps < 0 || h <= 0 || w <= 0) return fail(MVSDF_ERR_INVALID, "bad depth-map shape");
+  const long long total = (long long)n_maps * h * w;
+  if (total == 0) return MVSDF_OK;
+  if (!depths || !k_inv || !e_inv || !center || !size || !out_pts || !out_valid) return fail(MVSDF_ERR_INVALID, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  note_launch();
+  depth_backproject_kernel<<<(unsigned)((total + kBlk - 1) / kBlk), kBlk, 0, st>>>(depths, k_inv, e_inv, n_maps, h, w, center,
+                                                                               size, out_pts, out_valid);
+  return check_cuda(cudaGetLastError(), "launch depth_backproject_kernel");
+}
 
 size_t mvsdf_shade_workspace_bytes(int64_t n_rays, int feature_size) { return shade_layout(n_rays, feature_size).total + 256; }
 

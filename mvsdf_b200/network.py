@@ -8,9 +8,10 @@ code/model/implicit_differentiable_renderer.py:179-322, but every stage runs in
 libmvsdf_b200.so (hand-written sm_100a CUDA behind the C ABI of include/mvsdf_b200.h).
 PyTorch only owns the device buffers and the stream.
 
-Scope of this round: the forward path.  Outputs are plain tensors without an
-autograd graph; the fused backward and the phase-0 depth-surface
-samples (row f2, train_progress < 1/6) are not built yet and raise NotImplementedError.
+Scope of this round: the forward path, all three training phases included (the
+phase-0 depth-surface samples of :226-251 take their randomness from the caller or draw it like
+the reference).  Outputs are plain tensors without an autograd graph; the fused backward
+ is not built yet.
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ import os
 from ctypes import byref, c_void_p
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -291,9 +293,47 @@ class B200IDRNetwork(nn.Module):
         self.last_trace_counters = counters
         return ray_dirs, cam_loc, dists, net_mask, points
 
+    # ------------------------------------------------------------------ depth-surface samples (phase 0)
+    def depth_surface_samples(self, input, n_samples: int, dsurf_rand=None):
+        """implicit_differentiable_renderer.py:226-247.  Back-projection in mvsdf_depth_backproject; the data-dependent
+        boolean-mask compaction and the sorted np.random.choice sub-sampling need the surviving counts on the host, as
+        in the reference.  dsurf_rand = dict(jitter01 [m,3], idx_on [n], idx_jitter [n]) replays given draws; otherwise
+        they are drawn like the reference does (torch.rand_like on the device, np.random.choice)."""
+        L = _lib.lib()
+        depths = ops._f32(input["depths"])
+        cams = ops._f32(input["depth_cams"])
+        dev = depths.device
+        d = depths.reshape(-1, *depths.shape[-2:]).contiguous()                 # [n_maps,h,w]  (nv1hw -> N,h,w)
+        cams = cams.reshape(-1, 2, 4, 4)
+        n_maps, h, w = d.shape
+        k_inv = torch.inverse(cams[:, 1, :3, :3]).contiguous()
+        e_inv = torch.inverse(cams[:, 0]).contiguous()
+        center = ops._f32(input["center"]).reshape(-1, 3)[0].contiguous()
+        size = ops._f32(input["size"]).reshape(-1)[:1].contiguous()
+        pts = torch.empty(n_maps * h * w, 3, dtype=torch.float32, device=dev)
+        valid = torch.empty(n_maps * h * w, dtype=torch.uint8, device=dev)
+        _lib.check(L.mvsdf_depth_backproject(_lib.ptr(d), _lib.ptr(k_inv), _lib.ptr(e_inv), n_maps, h, w, _lib.ptr(center),
+                                             _lib.ptr(size), _lib.ptr(pts), _lib.ptr(valid),
+                                             c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        ds_norm = pts[valid.bool()]
+        rnd = dsurf_rand or {}
+        jitter01 = rnd.get("jitter01")
+        jitter01 = torch.rand_like(ds_norm) if jitter01 is None else jitter01.to(device=dev, dtype=torch.float32)
+        jitter_rad = 0.1                                                      # :227 (hard-coded in the reference)
+        ds_jit = ds_norm + jitter01 * jitter_rad * 2 - jitter_rad
+        out = []
+        for ds, key in ((ds_norm, "idx_on"), (ds_jit, "idx_jitter")):
+            inbound = (ds.abs() < self.object_bounding_sphere).float().sum(-1) > 2.9
+            ds_in = ds[inbound]
+            idx = rnd.get(key)
+            if idx is None:
+                idx = np.sort(np.random.choice(ds_in.shape[0], n_samples, replace=False))
+            out.append(ds_in[torch.as_tensor(np.asarray(idx), dtype=torch.long, device=dev)].contiguous())
+        return out[0], out[1]
+
     # ------------------------------------------------------------------ IDRNetwork.forward
     @torch.no_grad()
-    def forward(self, input, train_progress=None, steps01=None, eik_points=None):
+    def forward(self, input, train_progress=None, steps01=None, eik_points=None, dsurf_rand=None):
         L = _lib.lib()
         conf = self.schedule
         uv = ops._f32(input["uv"])
@@ -312,12 +352,15 @@ class B200IDRNetwork(nn.Module):
         rend_net = self.rendering_network.packed()
         obj_u8 = object_mask.to(torch.uint8).contiguous()
         training = self.training
+        use_dsurf = False
         if training:
             assert train_progress is not None
-            if any([conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
-                    conf.eik_use_dsurf_on(train_progress), conf.eik_use_dsurf_jitter(train_progress)]):
-                raise NotImplementedError("depth-surface samples (train_progress < 1/6, "
-                                          "implicit_differentiable_renderer.py:226-251) are SURVEY section 8 row f2")
+            flags = [conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
+                     conf.eik_use_dsurf_on(train_progress), conf.eik_use_dsurf_jitter(train_progress)]
+            use_dsurf = any(flags)
+            if use_dsurf and not all(flags):
+                raise NotImplementedError("schedules that enable only some of d_use_dsurf_* / eik_use_dsurf_* "
+                                          "(model/conf.py ships them switched together)")
         ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics, obj_u8, training, steps01)
         network_object_mask = net_u8.bool()
         surface_u8 = (net_u8 & obj_u8) if training else net_u8
@@ -360,12 +403,16 @@ class B200IDRNetwork(nn.Module):
                 r = self.object_bounding_sphere      # :216-221, CPU generator then .cuda()
                 eik_points = torch.empty(n_eik, 3).uniform_(-r, r)
             eik_points = eik_points.to(device=dev, dtype=torch.float32).contiguous()
-            extra, g_eik = ops.sdf_value_grad(sdf_net, eik_points, ops.HEAD_FULL)
+            extra_pts = eik_points
+            if use_dsurf:                                # :226-251: on-surface and jittered depth samples join the set
+                ds_on, ds_jit = self.depth_surface_samples(input, n_eik, dsurf_rand)
+                extra_pts = torch.cat([eik_points, ds_on, ds_jit], dim=0).contiguous()
+            extra, g_extra = ops.sdf_value_grad(sdf_net, extra_pts, ops.HEAD_FULL)
             f_s = surf_head[:M, 0:1]
-            eik_pts = torch.cat([diff_surf_pts, eik_points], dim=0)
+            eik_pts = torch.cat([diff_surf_pts, extra_pts], dim=0)
             output["eikonal_output"] = torch.cat([f_s, extra[:, :1]], dim=0).view(1, -1)
             output["eikonal_points_hom"] = torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1)
             keep = object_mask_true[hit_index[:M].long()]
-            output["surf_indicator_output"] = torch.cat([surf_head[:M, 1][keep], extra[:, 1]], dim=0)
-            output["grad_theta"] = torch.cat([normals[:M], g_eik], dim=0)
+            output["surf_indicator_output"] = torch.cat([surf_head[:M, 1][keep], extra[:n_eik, 1]], dim=0)
+            output["grad_theta"] = torch.cat([normals[:M], g_extra], dim=0)
         return output

@@ -195,6 +195,33 @@ def make_feature_maps(pose: torch.Tensor, intrinsics: torch.Tensor, h: int, w: i
     return out.contiguous()
 
 
+def make_depth_maps(pose: torch.Tensor, intrinsics: torch.Tensor, h: int, w: int, scale: int = 2,
+                    radius: float = 0.6):
+    """Synthetic MVS depth maps of the analytic sphere (no RNG): z-depth at the (1/scale)-resolution pixel centres,
+    0 where the ray misses, and the matching depth cameras [n,1,2,4,4] = (world->cam extrinsic, K / scale) -- the layout
+    of ground_truth['depths'] / ['depth_cams'] (datasets/scene_dataset.py:105-116, :205-206)."""
+    n = pose.shape[0]
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing="ij")
+    depths = torch.zeros(n, 1, 1, h, w, dtype=torch.float32)
+    cams = torch.zeros(n, 1, 2, 4, 4, dtype=torch.float32)
+    for i in range(n):
+        K = intrinsics[i].double().clone()
+        K[:2, :3] /= scale
+        P = pose[i].double()
+        d_cam = torch.stack([(xs + 0.5 - K[0, 2]) / K[0, 0], (ys + 0.5 - K[1, 2]) / K[1, 1], torch.ones_like(xs)], dim=-1)
+        d_w = d_cam @ P[:3, :3].T
+        c = P[:3, 3]
+        a = (d_w * d_w).sum(-1)
+        b = (d_w * c).sum(-1)
+        disc = b * b - a * (c.dot(c) - radius * radius)
+        z = torch.where(disc > 0, (-b - torch.sqrt(disc.clamp_min(0))) / a, torch.zeros_like(a))
+        depths[i, 0, 0] = z.float()
+        cams[i, 0, 0] = torch.linalg.inv(P).float()
+        cams[i, 0, 1] = torch.eye(4)
+        cams[i, 0, 1, :3, :3] = K[:3, :3].float()
+    return depths, cams
+
+
 def make_scene(H: int, W: int, n_images: int = 1, n_src: int = 1, n_rays: Optional[int] = None,
                seed: int = 0, mask_mode: str = "ones") -> Dict[str, torch.Tensor]:
     """A mini-batch in the layout IDRNetwork.forward / IDRLoss.forward consume
@@ -233,4 +260,5 @@ def make_scene(H: int, W: int, n_images: int = 1, n_src: int = 1, n_rays: Option
         "center": torch.zeros(B, 3),
         "rgb": (torch.rand(B, N, 3, generator=g) * 2 - 1).contiguous(),
     }
+    scene["depths"], scene["depth_cams"] = make_depth_maps(pose[:B], intr[:B], h, w)
     return scene

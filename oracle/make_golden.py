@@ -53,22 +53,39 @@ def npify(d):
 
 
 class UniformLog:
-    """Records the CPU-generator draws the reference makes inside forward (fact 0.10)."""
+    """Records the CPU-generator draws the reference makes inside forward (fact 0.10): Tensor.uniform_ (tracer steps,
+    eikonal points), torch.rand_like (depth-surface jitter, :240) and np.random.choice (depth-surface sub-sampling, :245)."""
 
     def __enter__(self):
-        self.draws = []
+        self.draws, self.rand_like, self.choices = [], [], []
         self._orig = torch.Tensor.uniform_
+        self._orig_rl = torch.rand_like
+        self._orig_ch = np.random.choice
 
         def logged(t, *a, **k):
             r = self._orig(t, *a, **k)
             self.draws.append(r.clone())
             return r
 
+        def logged_rl(t, *a, **k):
+            r = self._orig_rl(t, *a, **k)
+            self.rand_like.append(r.clone())
+            return r
+
+        def logged_ch(*a, **k):
+            r = self._orig_ch(*a, **k)
+            self.choices.append(np.sort(np.array(r)))
+            return r
+
         torch.Tensor.uniform_ = logged
+        torch.rand_like = logged_rl
+        np.random.choice = logged_ch
         return self
 
     def __exit__(self, *exc):
         torch.Tensor.uniform_ = self._orig
+        torch.rand_like = self._orig_rl
+        np.random.choice = self._orig_ch
 
 
 def case_forward(ref, name, preset, H, W, n_images, n_src, n_rays, training, tp, seed, mask_mode="ones"):
@@ -76,7 +93,10 @@ def case_forward(ref, name, preset, H, W, n_images, n_src, n_rays, training, tp,
     scene = synth.make_scene(H, W, n_images=n_images, n_src=n_src, n_rays=n_rays, seed=seed, mask_mode=mask_mode)
     model.train(training)
     inp = {k: scene[k].clone() for k in ["uv", "pose", "intrinsics", "object_mask"]}
+    if training:      # ground-truth tensors idr_train.py:262-266 moves into model_input for the phase-0 depth-surface samples
+        inp.update({k: scene[k].clone() for k in ["depths", "depth_cams", "center", "size"]})
     torch.manual_seed(4321 + seed)
+    np.random.seed(1234 + seed)
     with ref_shim.quiet(), UniformLog() as log:
         out = model(inp, tp)
     loss_mod = ref.loss.IDRLoss()
@@ -110,6 +130,12 @@ def case_forward(ref, name, preset, H, W, n_images, n_src, n_rays, training, tp,
         else:
             assert len(draws) == 1
             res["eik_points"] = draws[0]
+        if log.rand_like:            # phase 0: depth-surface samples
+            assert len(log.rand_like) == 1 and len(log.choices) == 2
+            res["dsurf_jitter01"] = log.rand_like[0]
+            res["dsurf_idx_on"] = log.choices[0]
+            res["dsurf_idx_jitter"] = log.choices[1]
+            res["eikonal_points_hom"] = out["eikonal_points_hom"]
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **npify(res))
     print(f"{name}: hits {int(nm.sum())}/{nm.numel()}  rgb_loss {float(rgb_l):.6f}  feat_loss {float(feat_l):.6f}")
 
@@ -168,6 +194,8 @@ def main():
     case_forward(ref, "cfg1_eval_w256", "w256", 32, 32, 1, 1, None, False, None, seed=0)
     case_forward(ref, "cfg1_train_w256", "w256", 32, 32, 2, 1, 512, True, 0.5, seed=0, mask_mode="disc")
     case_forward(ref, "small_eval_w512", "w512", 20, 20, 1, 2, None, False, None, seed=3)
+    # phase 0 (train_progress < 1/6): depth-surface samples join the eikonal set (:226-251)
+    case_forward(ref, "train_phase0_w256", "w256", 64, 64, 2, 1, 256, True, 0.1, seed=5, mask_mode="disc")
 
 
 if __name__ == "__main__":

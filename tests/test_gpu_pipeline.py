@@ -87,6 +87,33 @@ def test_train_forward_vs_reference_golden(golden):
         assert rel_err(losses["feat_loss"].cpu(), g["feat_loss"]) < 2e-2
 
 
+def test_train_phase0_forward_vs_reference_golden(golden):
+    """train_progress < 1/6: depth-surface samples (on the MVS depth surface and jittered around it) join the eikonal
+    set (implicit_differentiable_renderer.py:226-251); the reference's rand_like / np.random.choice draws are replayed."""
+    g = golden("train_phase0_w256")
+    dev = torch.device("cuda:0")
+    model, sd = _model(str(g["meta_preset"]), dev)
+    scene = scene_from_meta(g)
+    model.train()
+    keys = ["uv", "pose", "intrinsics", "object_mask", "depths", "depth_cams", "center", "size"]
+    rnd = dict(jitter01=t(g["dsurf_jitter01"]), idx_on=g["dsurf_idx_on"], idx_jitter=g["dsurf_idx_jitter"])
+    out = model(_to(scene, keys, dev), float(g["meta_tp"]), steps01=t(g["steps01"]), eik_points=t(g["eik_points"]),
+                dsurf_rand=rnd)
+    flips = _check_forward(out, g, scene, True)
+    n_hit = int(t(g["network_object_mask"]).sum())
+    # the depth-surface rows are independent of the tracer's decisions: compare them even if a ray flipped
+    hom = out["eikonal_points_hom"].cpu().reshape(-1, 4)
+    ref_hom = t(g["eikonal_points_hom"]).reshape(-1, 4)
+    n_extra = ref_hom.shape[0] - n_hit
+    assert (hom[-n_extra:] - ref_hom[-n_extra:]).abs().max().item() < 2e-6
+    assert (out["eikonal_output"].cpu().reshape(-1)[-n_extra:] - t(g["eikonal_output"]).reshape(-1)[-n_extra:]).abs().max().item() < 5e-5
+    assert (out["grad_theta"].cpu()[-n_extra:] - t(g["grad_theta"])[-n_extra:]).abs().max().item() < 5e-3
+    if flips == 0:
+        assert out["grad_theta"].shape == tuple(g["grad_theta"].shape)
+        assert (out["grad_theta"].cpu() - t(g["grad_theta"])).abs().max().item() < 5e-3
+        assert (out["surf_indicator_output"].cpu() - t(g["surf_indicator_output"])).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("name", ["tracer_eval_w256", "tracer_train_w256", "tracer_eval_w256_geo"])
 def test_tracer_vs_reference_golden(golden, name):
     g = golden(name)

@@ -50,7 +50,7 @@ def test_tracer_golden(golden, name):
     assert cnt.total > 0
 
 
-@pytest.mark.parametrize("name", ["cfg1_eval_w256", "cfg1_train_w256", "small_eval_w512"])
+@pytest.mark.parametrize("name", ["cfg1_eval_w256", "cfg1_train_w256", "small_eval_w512", "train_phase0_w256"])
 def test_forward_golden(golden, name):
     g = golden(name)
     sd = preset_state_dict(str(g["meta_preset"]), g["meta_weights_sha"])
@@ -61,6 +61,8 @@ def test_forward_golden(golden, name):
     kw = {}
     if training:
         kw = dict(steps01=t(g["steps01"]) if "steps01" in g else None, eik_points=t(g["eik_points"]))
+        if "dsurf_jitter01" in g:       # phase 0: the reference's rand_like / np.random.choice draws
+            kw["dsurf_rand"] = dict(jitter01=t(g["dsurf_jitter01"]), idx_on=g["dsurf_idx_on"], idx_jitter=g["dsurf_idx_jitter"])
     out = O.idr_forward(sw, rw, scene, tp, training, **kw)
     nm = out["network_object_mask"]
     assert torch.equal(nm, t(g["network_object_mask"]))
@@ -70,11 +72,17 @@ def test_forward_golden(golden, name):
     assert torch.allclose(out["diff_surf_pts"], t(g["diff_surf_pts"]), rtol=1e-5, atol=1e-5)
     losses = O.hot_path_losses(out, scene, 0.5 if tp is None else tp)
     assert rel_err(losses["rgb_loss"], g["rgb_loss"]) < 1e-5
+    if tp is not None and tp < O.PHASE[0]:     # loss.py:196-199 switches the term off in phase 0; the fixture still holds its value
+        losses["feat_loss"] = O.feat_loss_corr(out["diff_surf_pts"], scene["feat"], scene["cam"], scene["feat_src"],
+                                               scene["src_cams"], scene["size"][:1], scene["center"][:1], nm, out["object_mask"])
     assert rel_err(losses["feat_loss"], g["feat_loss"]) < 1e-4
     if training:
         assert torch.allclose(out["grad_theta"], t(g["grad_theta"]), rtol=1e-4, atol=1e-5)
         assert rel_err(losses["eikonal_loss"], g["eikonal_loss"]) < 1e-4
         assert rel_err(losses["surf_loss"], g["surf_loss"]) < 1e-5
+        if "eikonal_points_hom" in g:
+            assert torch.allclose(out["eikonal_points_hom"], t(g["eikonal_points_hom"]), rtol=1e-5, atol=1e-6)
+            assert torch.allclose(out["eikonal_output"], t(g["eikonal_output"]), rtol=1e-4, atol=2e-6)
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
