@@ -53,13 +53,20 @@ class B200IDRLoss(nn.Module):
         self.last_partials: Dict[str, torch.Tensor] = {}
 
     # ---- loss.py:21-28
-    @torch.no_grad()
     def get_rgb_loss(self, rgb_values, rgb_gt, network_object_mask, object_mask, reduce_fn=None):
+        mask = network_object_mask & object_mask
+        if torch.is_grad_enabled() and rgb_values.requires_grad:
+            from .autograd import RgbL1
+            return RgbL1.apply(self, rgb_values, rgb_gt.to(rgb_values.device), mask, reduce_fn)
+        return self._rgb_loss_native(rgb_values, rgb_gt, mask, reduce_fn)
+
+    @torch.no_grad()
+    def _rgb_loss_native(self, rgb_values, rgb_gt, mask, reduce_fn=None):
         L = _lib.lib()
         dev = rgb_values.device
         rgb_values = ops._f32(rgb_values)
         rgb_gt = ops._f32(rgb_gt.to(dev)).reshape(-1, 3)
-        mask = (network_object_mask & object_mask).to(torch.uint8).contiguous()
+        mask = mask.to(torch.uint8).contiguous()
         R = mask.shape[0]
         partial = torch.empty(2, dtype=torch.float64, device=dev)
         out = torch.empty((), dtype=torch.float32, device=dev)
@@ -72,18 +79,28 @@ class B200IDRLoss(nn.Module):
         return out
 
     # ---- loss.py:115-165 (uncerts is never produced by the reference: uncert_network is not instantiated)
-    @torch.no_grad()
     def get_feat_loss_corr(self, diff_surf_pts, uncerts, feat, cam, feat_src, src_cams, size, center,
                            network_object_mask, object_mask, hit_offsets: Optional[torch.Tensor] = None, reduce_fn=None):
         if uncerts is not None:
             raise NotImplementedError("the uncertainty branch (loss.py:156-159) is dead code in the reference")
-        L = _lib.lib()
         dev = diff_surf_pts.device
         B = feat.shape[0]
         if hit_offsets is None:
             m = (network_object_mask & object_mask).view(B, -1).sum(-1)
             hit_offsets = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), m.cumsum(0)]).to(torch.int32)
         hit_offsets = hit_offsets.to(device=dev, dtype=torch.int32).contiguous()
+        args = (diff_surf_pts, hit_offsets, feat.to(dev), cam.to(dev), feat_src.to(dev), src_cams.to(dev), size.to(dev),
+                center.to(dev), reduce_fn)
+        if torch.is_grad_enabled() and diff_surf_pts.requires_grad:
+            from .autograd import FeatConsistency
+            return FeatConsistency.apply(self, *args)
+        return self._feat_loss_native(*args)
+
+    @torch.no_grad()
+    def _feat_loss_native(self, diff_surf_pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn=None):
+        L = _lib.lib()
+        dev = diff_surf_pts.device
+        B = feat.shape[0]
         maps = self.store.get(feat.to(dev), feat_src.to(dev))
         _, V, h, w, C = maps.shape
         cams = torch.cat([cam.to(dev).unsqueeze(1), src_cams.to(dev)], dim=1).to(torch.float32).contiguous()   # [B,V,2,4,4]

@@ -10,8 +10,9 @@ PyTorch only owns the device buffers and the stream.
 
 Scope of this round: the forward path, all three training phases included (the
 phase-0 depth-surface samples of :226-251 take their randomness from the caller or draw it like
-the reference).  Outputs are plain tensors without an autograd graph; the fused backward
- is not built yet.
+the reference).  A training-mode call with autograd enabled returns the same native values attached
+to an autograd graph (mvsdf_b200/autograd.py: native forward, round-1 backward by PyTorch
+re-computation; the fused backward is SURVEY.md section 8 row f1).
 """
 from __future__ import annotations
 
@@ -332,8 +333,105 @@ class B200IDRNetwork(nn.Module):
         return out[0], out[1]
 
     # ------------------------------------------------------------------ IDRNetwork.forward
-    @torch.no_grad()
     def forward(self, input, train_progress=None, steps01=None, eik_points=None, dsurf_rand=None):
+        """implicit_differentiable_renderer.py:179-322.  Inference and no-grad calls run the fused native path;
+        a training-mode call with autograd enabled returns the same values attached to an autograd graph
+        (mvsdf_b200/autograd.py) so that the reference's ``loss.backward()`` reaches the parameters."""
+        wants_grad = (self.training and torch.is_grad_enabled()
+                      and any(p.requires_grad for p in self.parameters()))
+        if wants_grad:
+            return self._forward_autograd(input, train_progress, steps01, eik_points, dsurf_rand)
+        with torch.no_grad():
+            return self._forward_native(input, train_progress, steps01, eik_points, dsurf_rand)
+
+    def _phase0(self, train_progress) -> bool:
+        conf = self.schedule
+        flags = [conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
+                 conf.eik_use_dsurf_on(train_progress), conf.eik_use_dsurf_jitter(train_progress)]
+        if any(flags) and not all(flags):
+            raise NotImplementedError("schedules that enable only some of d_use_dsurf_* / eik_use_dsurf_* "
+                                      "(model/conf.py ships them switched together)")
+        return any(flags)
+
+    def _forward_autograd(self, input, train_progress, steps01, eik_points, dsurf_rand):
+        """Training forward with an autograd graph: the tracer (no_grad in the reference too, :192-198) is the native
+        persistent kernel; the differentiable stages are autograd.Functions whose FORWARD values are the native fused
+        kernels and whose backward is documented in mvsdf_b200/autograd.py."""
+        from .autograd import RenderEval, SdfEval
+        conf = self.schedule
+        assert train_progress is not None
+        uv, pose, intrinsics = ops._f32(input["uv"]), ops._f32(input["pose"]), ops._f32(input["intrinsics"])
+        dev = uv.device
+        if pose.shape[1] == 7:
+            raise NotImplementedError("quaternion poses (train_cameras=True) are outside the hot path")
+        object_mask_true = input["object_mask"].reshape(-1).to(device=dev, dtype=torch.bool)
+        object_mask = object_mask_true if conf.use_mask else torch.ones_like(object_mask_true)
+        B, N, _ = uv.shape
+        R = B * N
+        sdf_net = self.implicit_network.packed()
+        rend_net = self.rendering_network.packed()
+        with torch.no_grad():
+            ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics,
+                                                                  object_mask.to(torch.uint8).contiguous(), True, steps01)
+            sdf_out = ops.sdf_forward(sdf_net, points, ops.HEAD_SDF_ONLY)
+        network_object_mask = net_u8.bool()
+        surface_mask = network_object_mask & object_mask
+        idx = surface_mask.nonzero(as_tuple=False).squeeze(1)            # data-dependent size: one host sync, as in the reference
+        M = idx.shape[0]
+        x_s, t_s, d_s = points[idx], dists[idx].unsqueeze(-1), ray_dirs[idx]
+        c_s = cam_loc.unsqueeze(1).expand(B, N, 3).reshape(-1, 3)[idx]
+        sdf_p = [t for lin in self.implicit_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
+        rend_p = [t for lin in self.rendering_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
+        skip_in = self.implicit_network.skip_in
+
+        n_eik = R // 2
+        if eik_points is None:
+            r = self.object_bounding_sphere                      # :216-221, CPU generator then .cuda()
+            eik_points = torch.empty(n_eik, 3).uniform_(-r, r)
+        extra_pts = eik_points.to(device=dev, dtype=torch.float32).contiguous()
+        if self._phase0(train_progress):
+            ds_on, ds_jit = self.depth_surface_samples(input, n_eik, dsurf_rand)
+            extra_pts = torch.cat([extra_pts, ds_on, ds_jit], dim=0).contiguous()
+
+        full_s, g_s = SdfEval.apply(sdf_net, skip_in, 6, x_s, *sdf_p)            # :202 restricted to the surface rays, :275
+        full_e, g_e = SdfEval.apply(sdf_net, skip_in, 6, extra_pts, *sdf_p)      # :256, :275
+        f_s = full_s[:, :1]
+        eik_pts = torch.cat([x_s, extra_pts], dim=0)
+        keep = object_mask_true[idx]
+        # implicit differentiation (model/sample_network.py:10-20)
+        dot = (g_s.detach() * d_s).sum(-1, keepdim=True)
+        x_diff = c_s + (t_s - (f_s - f_s.detach()) / dot) * d_s
+        # get_rbg_value (:324-338)
+        full_d, n_d = SdfEval.apply(sdf_net, skip_in, 6, x_diff, *sdf_p)
+        feats = full_d[:, 2:]
+        p_in, n_in, v_in = x_diff, n_d, -d_s
+        if train_progress < conf.phase[0] or conf.disable_rgb_grad:
+            p_in, n_in, v_in = p_in.detach(), n_in.detach(), v_in.detach()
+        rgb_values = torch.ones(R, 3, dtype=torch.float32, device=dev)
+        if M > 0:
+            rgb_hit = RenderEval.apply(rend_net, 4, p_in, n_in, v_in, feats.contiguous(), *rend_p)
+            rgb_values = rgb_values.index_put((idx,), rgb_hit)
+        counts = surface_mask.view(B, -1).sum(-1)
+        hit_offsets = torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(torch.int32)
+        return {
+            "points": points,
+            "diff_surf_pts": x_diff,
+            "rgb_values": rgb_values,
+            "sdf_output": sdf_out.unsqueeze(1),
+            "network_object_mask": network_object_mask,
+            "object_mask": object_mask,
+            "object_mask_true": object_mask_true,
+            "grad_theta": torch.cat([g_s, g_e], dim=0),
+            "eikonal_points_hom": torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1),
+            "eikonal_output": torch.cat([f_s, full_e[:, :1]], dim=0).view(1, -1),
+            "surf_indicator_output": torch.cat([full_s[:, 1][keep], full_e[:n_eik, 1]], dim=0),
+            "hit_offsets": hit_offsets,
+            "surface_normals": n_d,
+            "ray_dirs": ray_dirs,
+            "dists": dists,
+        }
+
+    def _forward_native(self, input, train_progress=None, steps01=None, eik_points=None, dsurf_rand=None):
         L = _lib.lib()
         conf = self.schedule
         uv = ops._f32(input["uv"])
@@ -355,12 +453,7 @@ class B200IDRNetwork(nn.Module):
         use_dsurf = False
         if training:
             assert train_progress is not None
-            flags = [conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
-                     conf.eik_use_dsurf_on(train_progress), conf.eik_use_dsurf_jitter(train_progress)]
-            use_dsurf = any(flags)
-            if use_dsurf and not all(flags):
-                raise NotImplementedError("schedules that enable only some of d_use_dsurf_* / eik_use_dsurf_* "
-                                          "(model/conf.py ships them switched together)")
+            use_dsurf = self._phase0(train_progress)
         ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics, obj_u8, training, steps01)
         network_object_mask = net_u8.bool()
         surface_u8 = (net_u8 & obj_u8) if training else net_u8
