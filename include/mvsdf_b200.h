@@ -150,6 +150,20 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
                              const float* center, double* partials, void* stream);
 int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_loss, void* stream);
 
+/* ---- IDRLoss.get_depth_loss (code/model/loss.py:37-63) with carving_t2 + RunningTopK (code/utils/my_utils.py:168-201,
+ * :269-331), use_invalid=False, smooth=None: for every eikonal point, the signed gap to the MVS depth surface along the
+ * viewing rays of the n_views depth maps, the inside/outside vote (out_thresh_perc), the clamp to +-1.25 and the far/near
+ * attenuation weights.
+ *   eik_points [n_points, point_stride] (rows of eikonal_points_hom, normalised object frame; first 3 columns used),
+ *   eik_output [n_points] (SDF values), depths [n_views,h,w], depth_cams [n_views,2,4,4], size [1], center [3];
+ *   out_target [n_points] = -dist_r, out_weight [n_points] = far_weight * near_weight * in_range (what the backward needs:
+ *   d loss / d eik_output = weight * sign(eik_output - target) / n_points);
+ *   partials [2] float64 = (sum weight * |eik_output - target|, n_points); finalize with mvsdf_rgb_l1_finalize (sum / count). */
+int mvsdf_depth_loss_partials(const float* eik_points, int point_stride, const float* eik_output, int64_t n_points,
+                              const float* depths, const float* depth_cams, int n_views, int h, int w, const float* size,
+                              const float* center, float out_thresh_perc, float far_thresh, float far_att, float near_thresh,
+                              float near_att, float* out_target, float* out_weight, double* partials, void* stream);
+
 /* ---- IDRLoss.get_rgb_loss (loss.py:21-28): sum |rgb - gt| over mask / n_rays.  partials [2] float64 = (sum, n_rays). */
 int mvsdf_rgb_l1_partials(const float* rgb_values, const float* rgb_gt, const uint8_t* mask, int64_t n_rays,
                           double* partials, void* stream);

@@ -68,6 +68,9 @@ def _declare(lib):
     lib.mvsdf_feat_loss_partials.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
     lib.mvsdf_feat_loss_finalize.restype = c_int
     lib.mvsdf_feat_loss_finalize.argtypes = [P, c_int, P, P]
+    lib.mvsdf_depth_loss_partials.restype = c_int
+    lib.mvsdf_depth_loss_partials.argtypes = [P, c_int, P, c_int64, P, P, c_int, c_int, c_int, P, P, c_float, c_float, c_float,
+                                              c_float, c_float, P, P, P, P]
     lib.mvsdf_rgb_l1_partials.restype = c_int
     lib.mvsdf_rgb_l1_partials.argtypes = [P, P, P, c_int64, P, P]
     lib.mvsdf_rgb_l1_finalize.restype = c_int

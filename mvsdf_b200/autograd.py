@@ -9,7 +9,8 @@ Forward values always come from libmvsdf_b200.so (the fused tcgen05 kernels).  W
                       parameters, *including* the second-order terms the eikonal / normal paths need
                       (the reference gets them from ``create_graph=True``, :104).
 * ``RenderEval``   -- RenderingNetwork.forward (:145-167).
-* ``RgbL1`` / ``FeatConsistency`` -- IDRLoss.get_rgb_loss / get_feat_loss_corr (model/loss.py:21-28, :115-165).
+* ``RgbL1`` / ``FeatConsistency`` / ``DepthL1`` -- IDRLoss.get_rgb_loss / get_feat_loss_corr / get_depth_loss
+                      (model/loss.py:21-28, :115-165, :37-63).  RgbL1 and DepthL1 have closed-form backwards.
 
 ROUND-1 STATUS OF THE BACKWARD: the backward passes below RE-COMPUTE the op with plain PyTorch ops (cuBLAS SGEMMs,
 ``F.grid_sample``) inside ``backward`` and differentiate that -- a library path, not hand-written kernels.  It is only
@@ -136,6 +137,24 @@ class RgbL1(torch.autograd.Function):
         rgb_values, rgb_gt, mask, partial = ctx.saved_tensors          # partial = (sum, n_rays), global after the all-reduce
         d = torch.sign(rgb_values - rgb_gt.reshape(-1, 3)) * mask.unsqueeze(-1).to(rgb_values.dtype)
         return None, d * (g / partial[1].to(rgb_values.dtype)), None, None, None
+
+
+class DepthL1(torch.autograd.Function):
+    """loss = DepthL1.apply(loss_module, eik_points_hom, eik_output, depths, cams, size, center, tp, reduce_fn).
+    Forward = mvsdf_depth_loss_partials; the kernel also leaves the per-point target / weight, so the backward is the
+    closed form  d loss / d eik_output = weight * sign(eik_output - target) / n_points  (the points are detached, loss.py:38)."""
+
+    @staticmethod
+    def forward(ctx, module, pts_hom, eik_output, depths, cams, size, center, tp, reduce_fn):
+        out, target, weight = module._depth_loss_native(pts_hom, eik_output, depths, cams, size, center, tp, reduce_fn)
+        ctx.save_for_backward(eik_output, target, weight, module.last_partials["depth"])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        eik_output, target, weight, partial = ctx.saved_tensors
+        d = torch.sign(eik_output.reshape(-1) - target) * weight * (g / partial[1].to(weight.dtype))
+        return None, None, d.view_as(eik_output), None, None, None, None, None, None
 
 
 def _feat_loss_torch(pts, hit_offsets: List[int], counts, feat, cam, feat_src, src_cams, size, center):

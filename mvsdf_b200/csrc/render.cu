@@ -283,6 +283,104 @@ __global__ void feat_finalize_kernel(const double* __restrict__ partial, int B, 
   }
 }
 
+// ------------------------------------------------------------------ f2: depth-carving loss (loss.py:37-63, my_utils.py:269-331)
+// One thread per eikonal point: project into every MVS depth view (idx_world2cam, idx_cam2img, normalize_for_grid_sample,
+// get_in_range), nearest-neighbour depth lookup (grid_sample mode='nearest', zeros padding, align_corners=False), the
+// inside / outside vote of carving_t2 and its RunningTopK(k=1) aggregates (running min of the positive gaps, running max of
+// the negative ones, +-1e30/v sentinels), then the weights of get_depth_loss.  Writes the per-point L1 target (-dist_r)
+// and weight (far * near * in_range) for the backward pass and accumulates sum(weight * |f - target|).
+struct DepthArgs {
+  const float* pts;       // [E, stride] normalised object frame (eikonal_points_hom rows)
+  int pts_stride;
+  const float* f;         // [E] eikonal_output
+  const float* depths;    // [V,h,w]
+  const float* cams;      // [V,2,4,4]
+  const float* size;
+  const float* center;
+  int E, V, h, w;
+  float out_thresh_perc, far_thresh, far_att, near_thresh, near_att;
+  float* target;          // [E]
+  float* weight;          // [E]
+  double* partial;        // [2] = (sum, E)
+};
+
+__global__ void depth_carve_kernel(DepthArgs a) {
+  __shared__ double sh[kBlk / 32];
+  const float size = a.size[0];
+  const float cx = a.center[0], cy = a.center[1], cz = a.center[2];
+  const float big = 1e30f / (float)a.V;
+  double acc = 0.0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.E; e += gridDim.x * blockDim.x) {
+    const float* p = a.pts + (size_t)e * a.pts_stride;
+    const float X = __fadd_rn(__fmul_rn(__fmul_rn(p[0], 0.5f), size), cx);
+    const float Y = __fadd_rn(__fmul_rn(__fmul_rn(p[1], 0.5f), size), cy);
+    const float Z = __fadd_rn(__fmul_rn(__fmul_rn(p[2], 0.5f), size), cz);
+    int n_valid = 0, n_inside = 0;
+    float pos = big, neg = -big;
+    for (int v = 0; v < a.V; ++v) {
+      const float* cam = a.cams + (size_t)v * 32;
+      float c0 = dot4(cam, X, Y, Z, 1.f), c1 = dot4(cam + 4, X, Y, Z, 1.f), c2 = dot4(cam + 8, X, Y, Z, 1.f),
+            c3 = dot4(cam + 12, X, Y, Z, 1.f);
+      const float d0 = __fadd_rn(c3, 1e-9f);
+      c0 = __fdiv_rn(c0, d0);
+      c1 = __fdiv_rn(c1, d0);
+      c2 = __fdiv_rn(c2, d0);
+      c3 = __fdiv_rn(c3, d0);
+      const float point_depth = c2;
+      const float d1 = __fadd_rn(c3, 1e-9f);
+      const float x = __fdiv_rn(c0, d1), y = __fdiv_rn(c1, d1), z = __fdiv_rn(c2, d1);
+      const float* K = cam + 16;
+      float u = dot3(K, x, y, z), vv = dot3(K + 4, x, y, z), ww = dot3(K + 8, x, y, z);
+      const float d2 = __fadd_rn(ww, 1e-9f);
+      u = __fdiv_rn(u, d2);
+      vv = __fdiv_rn(vv, d2);
+      float gx = __fsub_rn(__fmul_rn(__fdiv_rn(u, (float)a.w), 2.f), 1.f);
+      float gy = __fsub_rn(__fmul_rn(__fdiv_rn(vv, (float)a.h), 2.f), 1.f);
+      gx = fminf(fmaxf(gx, -1.1f), 1.1f);
+      gy = fminf(fmaxf(gy, -1.1f), 1.1f);
+      const bool in = gx <= 1.f && gx >= -1.f && gy <= 1.f && gy >= -1.f;
+      // grid_sampler_2d, nearest: unnormalise with align_corners=False, round half to even
+      const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)a.w), 1.f), 0.5f);
+      const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)a.h), 1.f), 0.5f);
+      const int ix = (int)nearbyintf(fx), iy = (int)nearbyintf(fy);
+      float gd = 0.f;
+      if (ix >= 0 && ix < a.w && iy >= 0 && iy < a.h) gd = __ldg(a.depths + ((size_t)v * a.h + iy) * a.w + ix);
+      const bool valid = gd > 0.f && in;
+      const bool inside = valid && point_depth > __fmul_rn(gd, 0.99f);
+      const bool outside = valid && !inside;
+      const float dist = valid ? __fsub_rn(point_depth, gd) : 0.f;
+      n_valid += valid ? 1 : 0;
+      n_inside += inside ? 1 : 0;
+      pos = fminf(pos, inside ? dist : big);
+      neg = fmaxf(neg, outside ? dist : -big);
+    }
+    if (!(fabsf(pos) < big * 0.99f)) pos = big;
+    if (!(fabsf(neg) < big * 0.99f)) neg = -big;
+    const float outside_perc = __fdiv_rn((float)(n_valid - n_inside), __fadd_rn((float)n_valid, 1e-9f));
+    const bool scene_valid = n_valid > 0;
+    const bool scene_outside = scene_valid && outside_perc > a.out_thresh_perc;
+    const bool scene_inside = scene_valid && !scene_outside;
+    const float ave = __fadd_rn(scene_inside ? pos : 0.f, scene_outside ? neg : 0.f);
+    float dist_r = __fadd_rn(__fmul_rn(__fdiv_rn(ave, size), 2.f), scene_valid ? 0.f : -1.25f);
+    dist_r = fminf(fmaxf(dist_r, -1.25f), 1.25f);
+    const float far_w = fabsf(dist_r) > a.far_thresh ? a.far_att : 1.f;
+    const float near_w = fabsf(dist_r) < a.near_thresh ? a.near_att : 1.f;
+    const float wgt = scene_valid ? __fmul_rn(far_w, near_w) : 0.f;
+    const float tgt = -dist_r;
+    a.target[e] = tgt;
+    a.weight[e] = wgt;
+    acc += (double)__fmul_rn(fabsf(__fsub_rn(a.f[e], tgt)), wgt);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kBlk / 32; ++w) t += sh[w];
+    if (t != 0.0) atomicAdd(a.partial, t);
+  }
+}
+
 // ------------------------------------------------------------------ a16: rgb L1 over hit pixels / all pixels (loss.py:21-28)
 __global__ void rgb_l1_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, const uint8_t* __restrict__ mask,
                               long long R, double* __restrict__ partial) {
@@ -483,6 +581,26 @@ int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_lo
   if (!partials || !out_loss || n_images <= 0) return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_finalize: bad argument");
   note_launch(); feat_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_images, out_loss);
   return check_cuda(cudaGetLastError(), "feat_finalize launch");
+}
+
+int mvsdf_depth_loss_partials(const float* eik_points, int point_stride, const float* eik_output, int64_t n_points,
+                              const float* depths, const float* depth_cams, int n_views, int h, int w, const float* size,
+                              const float* center, float out_thresh_perc, float far_thresh, float far_att, float near_thresh,
+                              float near_att, float* out_target, float* out_weight, double* partials, void* stream) {
+  if (!eik_points || !eik_output || !depths || !depth_cams || !size || !center || !out_target || !out_weight || !partials ||
+      n_points <= 0 || n_views <= 0 || h <= 0 || w <= 0 || point_stride < 3)
+    return fail(MVSDF_ERR_INVALID, "mvsdf_depth_loss_partials: bad argument");
+  const int sms = sm_count();
+  if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = check_cuda(cudaMemsetAsync(partials, 0, sizeof(double) * 2, st), "memset partials");
+  if (rc) return rc;
+  note_launch(); set_double_kernel<<<1, 32, 0, st>>>(partials + 1, (double)n_points);
+  DepthArgs a{eik_points, point_stride, eik_output, depths, depth_cams, size, center, (int)n_points, n_views, h, w,
+              out_thresh_perc, far_thresh, far_att, near_thresh, near_att, out_target, out_weight, partials};
+  const int grid = (int)std::min<int64_t>((n_points + kBlk - 1) / kBlk, (int64_t)sms * 8);
+  note_launch(); depth_carve_kernel<<<grid, kBlk, 0, st>>>(a);
+  return check_cuda(cudaGetLastError(), "depth_carve launch");
 }
 
 int mvsdf_rgb_l1_partials(const float* rgb_values, const float* rgb_gt, const uint8_t* mask, int64_t n_rays,

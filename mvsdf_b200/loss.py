@@ -120,6 +120,54 @@ class B200IDRLoss(nn.Module):
         self.last_partials["feat"] = partial
         return out
 
+    # ---- loss.py:37-63 (+ carving_t2 / RunningTopK, utils/my_utils.py:168-201, :269-331)
+    def get_depth_loss(self, eikonal_points_hom, eikonal_output, depths, cams, size, center, far_thresh=None, far_att=None,
+                       near_thresh=None, near_att=None, smooth=None, train_progress=None, reduce_fn=None):
+        """Same positional signature as the reference; the attenuation arguments default to the schedule's values at
+        `train_progress`.  Unlike the reference, eikonal_points_hom is NOT rewritten in place (loss.py:42 does that through
+        detach(), a side effect nothing reads)."""
+        conf = self.schedule
+        if conf.use_invalid:
+            raise NotImplementedError("use_invalid=True (carving_t, my_utils.py:204-266) is off in model/conf.py:16")
+        if smooth is not None:
+            raise NotImplementedError("the SmoothL1 variant (loss.py:57-58) is never selected: conf.smooth(tp) is None")
+        tp = 1.0 if train_progress is None else train_progress
+        att = (conf.far_thresh if far_thresh is None else far_thresh, conf.far_att(tp) if far_att is None else far_att,
+               conf.near_thresh if near_thresh is None else near_thresh, conf.near_att(tp) if near_att is None else near_att)
+        dev = eikonal_output.device
+        args = (eikonal_points_hom, eikonal_output, depths.to(dev), cams.to(dev), size.to(dev), center.to(dev), att, reduce_fn)
+        if torch.is_grad_enabled() and eikonal_output.requires_grad:
+            from .autograd import DepthL1
+            return DepthL1.apply(self, *args)
+        return self._depth_loss_native(*args)[0]
+
+    @torch.no_grad()
+    def _depth_loss_native(self, eikonal_points_hom, eikonal_output, depths, cams, size, center, att, reduce_fn=None):
+        L = _lib.lib()
+        dev = eikonal_output.device
+        pts = ops._f32(eikonal_points_hom).reshape(-1, 4)
+        f = ops._f32(eikonal_output).reshape(-1)
+        E = f.shape[0]
+        d = ops._f32(depths).reshape(-1, *depths.shape[-2:])                     # nv1hw -> [V,h,w] (v = 1 per image)
+        c = ops._f32(cams).reshape(-1, 2, 4, 4)
+        V, h, w = d.shape
+        size = ops._f32(size).reshape(-1)[:1].contiguous()
+        center = ops._f32(center).reshape(-1)[:3].contiguous()
+        target = torch.empty(E, dtype=torch.float32, device=dev)
+        weight = torch.empty(E, dtype=torch.float32, device=dev)
+        partial = torch.empty(2, dtype=torch.float64, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.mvsdf_depth_loss_partials(_lib.ptr(pts), 4, _lib.ptr(f), E, _lib.ptr(d), _lib.ptr(c), V, h, w, _lib.ptr(size),
+                                               _lib.ptr(center), float(self.schedule.out_thresh_perc), float(att[0]), float(att[1]),
+                                               float(att[2]), float(att[3]), _lib.ptr(target), _lib.ptr(weight), _lib.ptr(partial),
+                                               stream))
+        if reduce_fn is not None:
+            reduce_fn(partial)
+        _lib.check(L.mvsdf_rgb_l1_finalize(_lib.ptr(partial), _lib.ptr(out), stream))
+        self.last_partials["depth"] = partial
+        return out, target, weight
+
     # ---- loss.py:30-35, :167-174 (elementwise reductions on small tensors)
     def get_eikonal_loss(self, grad_theta):
         if grad_theta.shape[0] == 0:
@@ -153,7 +201,19 @@ class B200IDRLoss(nn.Module):
             res["surf_loss"] = self.get_surf_loss(model_outputs["surf_indicator_output"], nm, model_outputs["object_mask_true"])
         return res
 
-    def forward(self, model_outputs, ground_truth, train_progress, n_img):
-        raise NotImplementedError(
-            "IDRLoss.forward needs the depth-carving term (loss.py:37-63), SURVEY.md section 8 row f2; "
-            "use hot_path_losses() for the rgb / feature-consistency / eikonal / surface-indicator terms")
+    def forward(self, model_outputs, ground_truth, train_progress, n_img=None, reduce_fn=None):
+        """IDRLoss.forward (loss.py:176-219): the five terms, their schedule-dependent weights and the reference's dict."""
+        conf = self.schedule
+        dev = model_outputs["rgb_values"].device
+        zero = lambda: torch.zeros(1, dtype=torch.float32, device=dev)
+        part = self.hot_path_losses(model_outputs, ground_truth, train_progress, reduce_fn=reduce_fn)
+        rgb_loss, feat_loss = part["rgb_loss"], part["feat_loss"]
+        eikonal_loss = part["eikonal_loss"]
+        depth_loss = self.get_depth_loss(model_outputs["eikonal_points_hom"], model_outputs["eikonal_output"],
+                                         ground_truth["depths"], ground_truth["depth_cams"], ground_truth["size"],
+                                         ground_truth["center"], train_progress=train_progress, reduce_fn=reduce_fn)
+        surf_loss = part["surf_loss"] if conf.phase[0] <= train_progress else zero()      # :201-204
+        loss = (rgb_loss * conf.rgb_weight(train_progress) + eikonal_loss * conf.eikonal_weight + surf_loss * conf.surf_weight
+                + feat_loss * conf.feat_weight(train_progress) + depth_loss * conf.depth_weight(train_progress))
+        return {"loss": loss, "rgb_loss": rgb_loss, "eikonal_loss": eikonal_loss, "depth_loss": depth_loss,
+                "feat_loss": feat_loss, "surf_loss": surf_loss}

@@ -177,6 +177,23 @@ class ImplicitNetwork(_PackedMlp):
         return ops.sdf_forward(self.packed(), input, ops.HEAD_FULL)
 
     @torch.no_grad()
+    def sdf_grid(self, resolution: int, bound: float = 1.0, chunk: int = 1 << 24) -> torch.Tensor:
+        """SDF on a dense resolution^3 grid over [-bound, bound]^3 -- the evaluation utils/plots.py:113-163 (get_surface_trace /
+        get_grid_uniform) feeds to marching cubes, 50 000 points per MLP call there.  One launch of
+        the fused SDF-only-head kernel per `chunk` points; returns [resolution, resolution, resolution] indexed [x, y, z]
+        like np.meshgrid(x, y, z) flattened the way plots.py:182-190 does (xx, yy, zz = meshgrid; points = stack(ravel))."""
+        dev = self.lin0.weight_v.device
+        ax = torch.linspace(-bound, bound, resolution, device=dev)
+        net = self.packed()
+        out = torch.empty(resolution ** 3, dtype=torch.float32, device=dev)
+        # np.meshgrid default indexing='xy': arrays of shape [ny, nx, nz]; flatten order = (y, x, z)
+        yy, xx, zz = torch.meshgrid(ax, ax, ax, indexing="ij")
+        pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=1)
+        for s in range(0, pts.shape[0], chunk):
+            out[s:s + chunk] = ops.sdf_forward(net, pts[s:s + chunk].contiguous(), ops.HEAD_SDF_ONLY)
+        return out.view(resolution, resolution, resolution)
+
+    @torch.no_grad()
     def gradient(self, x):
         """[P,3] -> [P,1,3] (:96-107), computed by forward-mode tangents in the fused kernel."""
         _, g = ops.sdf_value_grad(self.packed(), x, ops.HEAD_SDF_ONLY)

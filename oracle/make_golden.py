@@ -121,6 +121,13 @@ def case_forward(ref, name, preset, H, W, n_images, n_src, n_rays, training, tp,
             res["surf_loss"] = loss_mod.get_surf_loss(out["surf_indicator_output"], nm, out["object_mask_true"])
         res["grad_theta"] = out["grad_theta"]
         res["eikonal_output"] = out["eikonal_output"]
+        res["eikonal_points_hom_all"] = out["eikonal_points_hom"].clone()
+        c = ref.conf
+        with ref_shim.quiet():      # get_depth_loss rewrites eikonal_points_hom in place (detach() shares storage): pass a copy
+            res["depth_loss"] = loss_mod.get_depth_loss(out["eikonal_points_hom"].clone(), out["eikonal_output"], scene["depths"],
+                                                        scene["depth_cams"], scene["size"][:1], scene["center"][:1],
+                                                        far_thresh=c.far_thresh, far_att=c.far_att(tp), near_thresh=c.near_thresh,
+                                                        near_att=c.near_att(tp), smooth=c.smooth(tp))
         res["surf_indicator_output"] = out["surf_indicator_output"]
         draws = log.draws
         # order of draws: [min-sdf steps (100) if that stage ran], eikonal points (n_eik x 3)

@@ -12,7 +12,7 @@ from oracle import mvsdf_oracle as O
 pytestmark = pytest.mark.gpu
 
 IN = ["uv", "pose", "intrinsics", "object_mask", "depths", "depth_cams", "center", "size"]
-GT = ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center"]
+GT = ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center", "depths", "depth_cams"]
 
 
 @pytest.mark.parametrize("tp", [0.3, 0.1])
@@ -36,7 +36,10 @@ def test_parameter_gradients_match_oracle_autograd(tp):
     ref = O.idr_forward(O.sdf_weights(params), O.render_weights(params), scene, tp, True, steps01=steps, eik_points=eik,
                         dsurf_rand=rnd)
     rl = O.hot_path_losses(ref, scene, tp)
-    ref_total = 0.5 * rl["rgb_loss"] + 0.1 * rl["eikonal_loss"] + 0.01 * rl["surf_loss"] + O.feat_weight(tp) * rl["feat_loss"].sum()
+    # the reference's total (loss.py:206-210); the surface-indicator term is switched off in phase 0 (:201-204)
+    surf_w = 0.01 if tp >= O.PHASE[0] else 0.0
+    ref_total = (0.5 * rl["rgb_loss"] + 0.1 * rl["eikonal_loss"] + surf_w * rl["surf_loss"]
+                 + O.feat_weight(tp) * rl["feat_loss"].sum() + rl["depth_loss"])
     ref_total.backward()
 
     # --- product path
@@ -48,12 +51,11 @@ def test_parameter_gradients_match_oracle_autograd(tp):
     assert out["rgb_values"].requires_grad and out["grad_theta"].requires_grad
     if int((out["network_object_mask"].cpu() != ref["network_object_mask"]).sum()) != 0:
         pytest.skip("a discrete tracer decision flipped on this input; gradient comparison is not meaningful")
-    loss = B200IDRLoss()
-    ls = loss.hot_path_losses(out, {k: scene[k].to(dev) for k in GT}, tp)
-    for k in ("rgb_loss", "eikonal_loss", "surf_loss"):
+    ls = B200IDRLoss()(out, {k: scene[k].to(dev) for k in GT}, tp, 2)          # the call of idr_train.py:269
+    for k in ("rgb_loss", "eikonal_loss", "depth_loss"):
         assert abs(float(ls[k]) - float(rl[k])) < 1e-3 * max(1.0, abs(float(rl[k]))), k
-    total = 0.5 * ls["rgb_loss"] + 0.1 * ls["eikonal_loss"] + 0.01 * ls["surf_loss"] + O.feat_weight(tp) * ls["feat_loss"].sum()
-    total.backward()
+    assert abs(float(ls["loss"]) - float(ref_total)) < 1e-3 * abs(float(ref_total))
+    ls["loss"].sum().backward()
     worst = 0.0
     for name, p in model.named_parameters():
         gr = params[name].grad

@@ -87,6 +87,44 @@ def test_train_forward_vs_reference_golden(golden):
         assert rel_err(losses["feat_loss"].cpu(), g["feat_loss"]) < 2e-2
 
 
+@pytest.mark.parametrize("name", ["cfg1_train_w256", "train_phase0_w256"])
+def test_depth_carving_loss_vs_reference_golden(golden, name):
+    """IDRLoss.get_depth_loss (loss.py:37-63, carving_t2) on the reference's own eikonal set."""
+    from mvsdf_b200.loss import B200IDRLoss
+    g = golden(name)
+    dev = torch.device("cuda:0")
+    scene = scene_from_meta(g)
+    tp = float(g["meta_tp"])
+    loss = B200IDRLoss()
+    dl = loss.get_depth_loss(t(g["eikonal_points_hom_all"]).to(dev), t(g["eikonal_output"]).to(dev), scene["depths"].to(dev),
+                             scene["depth_cams"].to(dev), scene["size"][:1].to(dev), scene["center"][:1].to(dev),
+                             train_progress=tp)
+    assert rel_err(dl.cpu(), g["depth_loss"]) < 1e-5
+
+
+def test_full_loss_dict_vs_reference_golden(golden):
+    """B200IDRLoss.forward returns the reference's dict (loss.py:212-219) with its schedule-dependent weights."""
+    from mvsdf_b200.loss import B200IDRLoss
+    from mvsdf_b200 import conf
+    g = golden("cfg1_train_w256")
+    dev = torch.device("cuda:0")
+    model, sd = _model(str(g["meta_preset"]), dev)
+    scene = scene_from_meta(g)
+    model.train()
+    tp = float(g["meta_tp"])
+    with torch.no_grad():
+        out = model(_to(scene, ["uv", "pose", "intrinsics", "object_mask"], dev), tp, steps01=t(g["steps01"]),
+                    eik_points=t(g["eik_points"]))
+    gt = _to(scene, ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center", "depths", "depth_cams"], dev)
+    res = B200IDRLoss()(out, gt, tp, 2)
+    assert set(res) == {"loss", "rgb_loss", "eikonal_loss", "depth_loss", "feat_loss", "surf_loss"}
+    if int((out["network_object_mask"].cpu() != t(g["network_object_mask"])).sum()) == 0:
+        assert rel_err(res["depth_loss"].cpu(), g["depth_loss"]) < 2e-3
+        want = (0.5 * float(g["rgb_loss"]) + conf.eikonal_weight * float(g["eikonal_loss"]) + conf.surf_weight * float(g["surf_loss"])
+                + conf.feat_weight(tp) * float(g["feat_loss"]) + float(g["depth_loss"]))
+        assert abs(float(res["loss"]) - want) < 2e-3 * abs(want)
+
+
 def test_train_phase0_forward_vs_reference_golden(golden):
     """train_progress < 1/6: depth-surface samples (on the MVS depth surface and jittered around it) join the eikonal
     set (implicit_differentiable_renderer.py:226-251); the reference's rand_like / np.random.choice draws are replayed."""

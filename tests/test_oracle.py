@@ -80,6 +80,11 @@ def test_forward_golden(golden, name):
         assert torch.allclose(out["grad_theta"], t(g["grad_theta"]), rtol=1e-4, atol=1e-5)
         assert rel_err(losses["eikonal_loss"], g["eikonal_loss"]) < 1e-4
         assert rel_err(losses["surf_loss"], g["surf_loss"]) < 1e-5
+        if "depth_loss" in g:     # depth-carving term (loss.py:37-63) on the reference's own eikonal set
+            dl = O.depth_loss(t(g["eikonal_points_hom_all"]), t(g["eikonal_output"]), scene["depths"], scene["depth_cams"],
+                              scene["size"][:1], scene["center"][:1], tp)
+            assert rel_err(dl, g["depth_loss"]) < 1e-5
+            assert rel_err(losses["depth_loss"], g["depth_loss"]) < 1e-4
         if "eikonal_points_hom" in g:
             assert torch.allclose(out["eikonal_points_hom"], t(g["eikonal_points_hom"]), rtol=1e-5, atol=1e-6)
             assert torch.allclose(out["eikonal_output"], t(g["eikonal_output"]), rtol=1e-4, atol=2e-6)
