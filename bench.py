@@ -129,6 +129,8 @@ def run_ours(args):
     model.load_state_dict(sd)
     model.train(cfg["training"])
     model.skip_min_sdf = bool(args.skip_min_sdf)
+    if args.prefilter_tau is not None:
+        model.prefilter_tau = float(args.prefilter_tau)
     loss_mod = B200IDRLoss()
     L = _lib.lib()
     tp = 0.5
@@ -185,7 +187,9 @@ def run_ours(args):
     value = world * R / (ms_per_step * 1e-3)
 
     # tracer evaluations of the last step (E_trace of SURVEY 8d: requests the reference algorithm issues)
-    evals = int(model.last_trace_counters.cpu().sum().item())
+    cnt = model.last_trace_counters.cpu()
+    evals = int(cnt[:252].sum().item())                          # include/mvsdf_b200.h: MVSDF_CTR_*
+    refined, violations = int(cnt[254]), int(cnt[255])
     n_hit = int(out["hit_offsets"][-1].item())
     width = cfg["width"]
     fl = FLOP[width]
@@ -237,7 +241,11 @@ def run_ours(args):
                                    f"+ feat loss + rgb L1", "rays_per_gpu": R, "hit_fraction": n_hit / R,
                        "tracer_evals_per_ray": evals / R, "parallelism": f"ray-sharded dp{world}, loss-partials all-reduce",
                        "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
-                       "skip_min_sdf": bool(args.skip_min_sdf)},
+                       "skip_min_sdf": bool(args.skip_min_sdf),
+                       "prefilter": {"tau": model.prefilter_tau, "refined_evals_per_ray": refined / R,
+                                     "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
+                                     "note": "100-sample stages: screening pass (1 fp16 product) over all samples + exact "
+                                             "pass (3 products) over the undecidable ones; outputs bit-identical to tau=0"}},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
@@ -339,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--skip-min-sdf", type=int, default=0)
+    ap.add_argument("--prefilter-tau", type=float, default=None, help="override B200IDRNetwork.prefilter_tau (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()

@@ -34,6 +34,9 @@ extern "C" {
 
 #define MVSDF_HEAD_SDF_ONLY 0
 #define MVSDF_HEAD_FULL 1
+#define MVSDF_HEAD_SDF_SCREEN 2   /* mvsdf_sdf_forward only: SDF column at screening precision (single fp16 product, ~1e-3
+                                     absolute error; the tracer's sampler prefilter).  Batches too small for the CTA-pair
+                                     kernel are evaluated exactly. */
 
 typedef struct mvsdf_net mvsdf_net;   /* host-side layout plan of one packed MLP; owns no device memory */
 
@@ -90,9 +93,21 @@ typedef struct mvsdf_tracer_params {
   int n_steps;            /* must be 100 */
   int n_secant_steps;
   int skip_min_sdf;       /* training only: drop minimal_sdf_points (:280-308), whose outputs no MVSDF loss reads */
+  float prefilter_tau;    /* 0 = off.  > 0: the 100-sample stages (ray_sampler :206-235, minimal_sdf_points :287-305) first
+                             evaluate all samples at screening precision and re-evaluate exactly only the samples whose sign
+                             (|sdf| < tau), secant end points or arg-min rank the screening value cannot decide.  Results
+                             are bit-identical to tau = 0 as long as the screening error stays below tau; out_counters
+                             [MVSDF_CTR_VIOLATIONS] counts refined samples whose screening error exceeded tau / 2 -- a
+                             caller that sees it non-zero repeats the call with tau = 0 (B200IDRNetwork does). */
 } mvsdf_tracer_params;
 
 #define MVSDF_NUM_TRACE_COUNTERS 256
+/* out_counters: slots [0, MVSDF_CTR_SAMPLER_RAYS) are the SDF evaluations the reference algorithm requests per phase (their
+ * sum is E_trace of SURVEY 8d, independent of the prefilter); the fixed slots: */
+#define MVSDF_CTR_SAMPLER_RAYS 252   /* rays that entered ray_sampler (ray_tracing.py:44-61) */
+#define MVSDF_CTR_MINSDF_RAYS 253    /* rays that entered minimal_sdf_points (:86-94), training only */
+#define MVSDF_CTR_REFINED 254        /* prefilter: samples evaluated a second time at full precision */
+#define MVSDF_CTR_VIOLATIONS 255     /* prefilter: refined samples with |screening - exact| > tau / 2 */
 
 size_t mvsdf_trace_workspace_bytes(int64_t n_rays, int n_images);
 
@@ -105,7 +120,7 @@ size_t mvsdf_trace_workspace_bytes(int64_t n_rays, int n_images);
  *   the CPU generator exactly like ray_tracing.py:287 (training only).
  * Outputs: out_ray_dirs [B*N,3], out_cam_loc [B,3] (optional), out_dists [B*N], out_net_mask [B*N] uint8
  *   (network_object_mask), out_points [B*N,3] (optional; cam_loc + dists*ray_dirs, :200 of the renderer),
- *   out_counters [MVSDF_NUM_TRACE_COUNTERS] int32 (optional; SDF evaluations requested per phase, their sum is E_trace). */
+ *   out_counters [MVSDF_NUM_TRACE_COUNTERS] int32 (optional; see MVSDF_CTR_*). */
 int mvsdf_trace(const mvsdf_net* sdf_net, const void* sdf_packed, const float* uv, const float* pose,
                 const float* intrinsics, const uint8_t* object_mask, const mvsdf_tracer_params* params, int n_images,
                 int n_pixels, int training, const float* linspace100, const float* steps01, size_t workspace_bytes,

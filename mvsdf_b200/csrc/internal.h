@@ -16,7 +16,7 @@ void note_launch();   // counts kernel launches made by the library (mvsdf_launc
 
 // MLP tile launches (mlp_abi.cu)
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,
-            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st);
+            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st, bool screening = false);
 int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const float* view, const float* normals,
                const float* feats, int feat_stride, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st);
 

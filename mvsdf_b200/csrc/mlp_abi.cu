@@ -222,7 +222,10 @@ template <int KIND, int MODE, int VER>
 static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, bool device_count, cudaStream_t st) {
   const int sms = sm_count();
   const size_t smem = mlp_smem_bytes(p.k_cores_max);
-  auto kern = VER == 2 ? mlp_pair2_kernel<KIND, MODE> : mlp_pair_kernel<KIND, MODE>;
+  // the screening-precision instantiation exists for the plain SDF evaluation only (the tracer's sampler prefilter)
+  constexpr bool kCanLp = KIND == NET_SDF && MODE == 0 && VER == 2;
+  auto kern = VER == 2 ? ((kCanLp && a.lp) ? mlp_pair2_kernel<KIND, MODE, kCanLp ? 1 : 0> : mlp_pair2_kernel<KIND, MODE, 0>)
+                       : mlp_pair_kernel<KIND, MODE>;
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(mlp_pair_kernel)");
   if (rc) return rc;
@@ -259,7 +262,7 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
 }
 
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,
-            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st) {
+            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st, bool screening) {
   if (!net || net->plan.kind != NET_SDF) return fail(MVSDF_ERR_INVALID, "expected an SDF net plan");
   if (n == 0 && !n_dev) return MVSDF_OK;   // empty batch: nothing to enqueue
   if (!packed || (!x && n > 0) || n < 0) return fail(MVSDF_ERR_INVALID, "null pointer / negative count");
@@ -273,6 +276,7 @@ int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n,
   a.out_sdf = out_sdf;
   a.out_full = out_full;
   a.out_grad = out_grad;
+  a.lp = (screening && !with_grad && head == HEAD_SDF_ONLY) ? 1 : 0;
   return with_grad ? launch_mlp<NET_SDF, 1>(net->plan, a, n, n_dev, st) : launch_mlp<NET_SDF, 0>(net->plan, a, n, n_dev, st);
 }
 
@@ -451,6 +455,9 @@ int mvsdf_pack_weights(const mvsdf_net* net, const float* const* weight_v_host, 
 
 int mvsdf_sdf_forward(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev,
                       int head, float* out_sdf, float* out_full, void* stream) {
+  if (head == MVSDF_HEAD_SDF_SCREEN)
+    return mlp_sdf(net, packed, x, n, n_dev, MVSDF_HEAD_SDF_ONLY, out_sdf, nullptr, nullptr, false,
+                   static_cast<cudaStream_t>(stream), true);
   return mlp_sdf(net, packed, x, n, n_dev, head, out_sdf, out_full, nullptr, false, static_cast<cudaStream_t>(stream));
 }
 

@@ -51,6 +51,7 @@ struct MlpArgs {
   int feat_size;
   int debug;                 // bit0 skip weight copies, bit1 skip UMMAs, bit2 skip epilogue math (bottleneck isolation only)
   int feat_stride;           // row stride (floats) of `feats`; lets the render pass read full[:, 2:] in place
+  int lp;                    // screening precision (pair2 kernel only): W_hi X_hi^T, see mlp_pair2_kernel.cuh
   long long n;               // number of points (ignored when n_ptr != nullptr)
   const int* n_ptr;          // optional device-side count
   const float* x;            // [n,3]
@@ -147,6 +148,13 @@ __device__ __forceinline__ void pack_split_fh(float y0, float y1, uint32_t& hi2,
       : "=r"(hi2), "=f"(l0), "=f"(l1)
       : "f"(y0), "f"(y1));
   asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo2) : "f"(l0), "f"(l1));
+}
+
+// fp16 hi parts only (screening precision)
+__device__ __forceinline__ uint32_t pack_hi(float y0, float y1) {
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(h) : "f"(y0), "f"(y1));
+  return h;
 }
 
 template <int KIND, int MODE, int CL>

@@ -47,7 +47,14 @@ __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, 
 #define P2_TRACE(role, index) do { } while (0)
 #endif
 
-template <int KIND, int MODE>
+// LP = 1: single-product "screening" precision -- only W_hi X_hi^T (fp16 operands, ~1e-3 absolute SDF error).  The pair
+// tile is 256 columns wide (128 points per CTA): the second 64 columns of a CTA live where the exact kernel keeps the lo
+// parts -- in the activation operand (feature-block slots 8-15, so one N=256 UMMA descriptor walk covers both) and in TMEM
+// (the D_b columns) -- so every buffer, barrier and byte count of the exact kernel is reused unchanged: one N=256 UMMA
+// per K step instead of three N=128 ones (2/3 of the tensor work for twice the points), the hi half of each weight
+// stage only.  Used by the tracer to decide which of the 100 samples per ray need the exact evaluation at all
+// (csrc/tracer.cu, prefilter); never for an output.
+template <int KIND, int MODE, int LP = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_pair2_kernel(const MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -72,7 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 
   const int n_dev_count = a.n_ptr ? __shfl_sync(0xffffffffu, *a.n_ptr, 0) : 0;
   const long long n_pts = a.n_ptr ? (long long)n_dev_count : a.n;
-  constexpr int kPtsPerCta = (MODE == 0) ? kTileN : kTileN / 4;       // points per CTA per tile
+  constexpr int kPtsPerCta = LP ? 2 * kTileN : ((MODE == 0) ? kTileN : kTileN / 4);       // points per CTA per tile
   const long long n_tiles = (n_pts + 2 * kPtsPerCta - 1) / (2 * kPtsPerCta);
   const long long pair0 = blockIdx.x >> 1;
   const long long pair_stride = gridDim.x >> 1;
@@ -116,11 +123,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
           const uint8_t* src = a.packed + lp.w_off + (size_t)m * lp.k_chunks * kStageBytes;
           for (int kc = k0; kc < k1; ++kc, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (a.debug & 16) ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            else ptx::mbar_wait_sleep(bar_empty + 8 * s, ph ^ 1);
             if (lane == 0) {
               if (have && !(a.debug & 1)) {
-                ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
-                ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)kc * kStageBytes, kStageBytes, bar_full + 8 * s);
+                constexpr uint32_t kCopy = LP ? kTileBytes : kStageBytes;      // LP: the hi tile only
+                ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kCopy);
+                ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)kc * kStageBytes, kCopy, bar_full + 8 * s);
               } else {
                 ptx::mbar_arrive(bar_full + 8 * s);     // odd tile count: this half multiplies stale data into rows nobody reads
               }
@@ -137,7 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     // (Merging the first two into one N = 256 UMMA over [X_hi ; X_lo] reads W_hi once and was measured 1 % faster, but
     //  the third product then lands on b for CTA 0's points and on a for CTA 1's: the fp32 rounding of a point would
     //  depend on which CTA processes it, and the outputs would no longer be bit-identical under re-sharding.)
-    constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, kP2Cols);
+    constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, LP ? 2 * kP2Cols : kP2Cols);
     const bool leader = ptx::elect_one();
     const uint32_t issue = (leader && !(a.debug & 2)) ? 1u : 0u;
     uint32_t it0 = 0, x_ctr = 0, d1_uses = 0;
@@ -207,7 +216,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
               const uint64_t da_lo = ptx::desc_from_words(a_off + ((kTileBytes + ks * 256) >> 4), dhi_a);
               const uint64_t db_hi = ptx::desc_from_words(b_off + ks * (2 * kBCoreStride >> 4), dhi_b);
               const uint64_t db_lo = ptx::desc_from_words(b_off + ((kBLoOffset + ks * 2 * kBCoreStride) >> 4), dhi_b);
-              ptx::umma3_f16_2cta(d_a, d_b, da_hi, da_lo, db_hi, db_lo, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
+              if (LP) ptx::umma1_f16_2cta(d_a, da_hi, db_hi, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
+              else ptx::umma3_f16_2cta(d_a, d_b, da_hi, da_lo, db_hi, db_lo, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
             }
             if (leader) ptx::umma_commit_2cta(bar_empty + 8 * st, 3);
             __syncwarp();
@@ -302,8 +312,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        for (int cidx = t; cidx < kTileN * 64; cidx += kEpiThreads) {
-          const int col = cidx >> 6, k = cidx & 63;
+        for (int cidx = t; cidx < (LP ? 2 * kTileN : kTileN) * 64; cidx += kEpiThreads) {
+          const int col = cidx >> 6, k = cidx & 63;        // LP: columns 64-127 fall into slots 8-15 of the feature block
           float v = 0.0f;
           if (k < a.pe_dim) {
             if (MODE == 0) {
@@ -316,7 +326,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
             }
           }
           const uint32_t o = xoff(col, k);
-          store_split(s_pehi + o, s_pelo + o, v * kActScale);
+          if (LP) ptx::st_shared_u16(s_pehi + o, __half_as_ushort(__float2half_rn(v * kActScale)));
+          else store_split(s_pehi + o, s_pelo + o, v * kActScale);
         }
       } else {
         if (t < kTileN) {
@@ -380,7 +391,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
         for (int mp = 0; mp < kP2Tiles; ++mp) {
           if (mp < n_pair_tiles) {
             if (tracer) P2_TRACE(1 + crank, tr + 4 * mp);          // waiting for D_mp
-            ptx::mbar_wait(bar_acc + 8 * mp, acc_ctr[mp] & 1);
+            if (a.debug & 16) ptx::mbar_wait(bar_acc + 8 * mp, acc_ctr[mp] & 1);
+            else ptx::mbar_wait_sleep(bar_acc + 8 * mp, acc_ctr[mp] & 1);
             ++acc_ctr[mp];
             ptx::tc_fence_after();
             if (tracer) P2_TRACE(1 + crank, tr + 4 * mp + 1);      // D_mp ready
@@ -394,8 +406,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
             for (int hcol = 0; hcol < 2; ++hcol) {
               const uint32_t dest_h = hcol == 0 ? (crank ^ 1u) : crank;     // peer columns first: their st.async overlaps my own half
               const uint32_t tcol = (uint32_t)(mp * 2 * kP2Cols) + dest_h * kTileN + (uint32_t)lcol0;
-              ptx::tmem_ld_32x16(t_row + tcol, va[hcol]);
-              ptx::tmem_ld_32x16(t_row + tcol + kP2Cols, vb[hcol]);
+              if (LP) {       // N = 256: columns [128 dest_h, +128) are dest_h's; vb = its second 64-column block
+                ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kP2Cols) + dest_h * (2 * kTileN) + (uint32_t)lcol0, va[hcol]);
+                ptx::tmem_ld_32x16(t_row + (uint32_t)(mp * 2 * kP2Cols) + dest_h * (2 * kTileN) + kTileN + (uint32_t)lcol0, vb[hcol]);
+              } else {
+                ptx::tmem_ld_32x16(t_row + tcol, va[hcol]);
+                ptx::tmem_ld_32x16(t_row + tcol + kP2Cols, vb[hcol]);
+              }
             }
             ptx::tmem_ld_wait();
             if (tracer) P2_TRACE(1 + crank, tr + 4 * mp + 2);      // drained
@@ -418,6 +435,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                   const float bias_k = bias * ((KIND == NET_SDF) ? kSpT : kActScale);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
+                    if (LP) {       // two independent column blocks; "plo" carries the hi parts of columns 64-127
+                      const float ta0 = fmaf(__uint_as_float(va[hcol][2 * i]), kK, bias_k);
+                      const float ta1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, bias_k);
+                      const float tb0 = fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k);
+                      const float tb1 = fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k);
+                      phi[i] = pack_hi(softplus_t_scaled(ta0), softplus_t_scaled(ta1));
+                      plo[i] = pack_hi(softplus_t_scaled(tb0), softplus_t_scaled(tb1));
+                      continue;
+                    }
                     const float t0 = fmaf(__uint_as_float(va[hcol][2 * i]), kK, fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k));
                     const float t1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k));
                     const float y0 = (KIND == NET_SDF && !(a.debug & 8)) ? softplus_t_scaled(t0) : fmaxf(t0, 0.0f);
@@ -461,6 +487,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int ccta = (int)dest_h, lc = lcol0 + j;   // owner CTA of the column and its index there
+                  if (LP) {       // SDF-only head, two column blocks
+                    const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;
+                    if (f == 0) {
+                      if (gp < n_pts) a.out_sdf[gp] = __uint_as_float(va[hcol][j]) * kInvScale + bias;
+                      if (gp + kTileN < n_pts) a.out_sdf[gp + kTileN] = __uint_as_float(vb[hcol][j]) * kInvScale + bias;
+                    }
+                    continue;
+                  }
                   const float acc = (__uint_as_float(va[hcol][j]) + __uint_as_float(vb[hcol][j])) * kInvScale;
                   if (KIND == NET_RENDER) {
                     const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;

@@ -37,6 +37,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// wait that lets the hardware suspend the warp (try_wait with a suspend-time hint, SASS: TRYWAIT + NANOSLEEP.SYNCS):
+// for waits that are long by construction -- a spinning warp costs issue slots and, at the power cap, SM clock
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!ok);
+}
 // non-blocking query of a phase
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -162,6 +176,18 @@ __device__ __forceinline__ void umma3_f16_2cta(uint32_t d_a, uint32_t d_b, uint6
       "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %4, %6, t;\n\t}"
       :
       : "r"(d_a), "r"(d_b), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+// single product (screening precision): D_a (+)= A_hi B_hi
+__device__ __forceinline__ void umma1_f16_2cta(uint32_t d_a, uint64_t a_hi, uint64_t b_hi, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_a), "l"(a_hi), "l"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {

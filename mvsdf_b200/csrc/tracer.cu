@@ -56,12 +56,20 @@ struct RayState {
   int* list_pos;     // position of a ray inside the list (sampler batches)
 };
 
+constexpr int kNumCounters = 256;
+// fixed slots of out_counters (include/mvsdf_b200.h): everything below kCtrSamplerRays is an SDF request count
+constexpr int kCtrSamplerRays = 252, kCtrMinSdfRays = 253, kCtrRefined = 254, kCtrViolations = 255;
+
 struct TraceCtx {
   RayState s;
   const float* cam;  // [B,3]
   float* req_pts;    // [cap,3]
   float* req_val;    // [cap]
-  int* counters;     // [kNumCounters]
+  float* ref_pts;    // [cap,3]   prefilter: samples that need the exact evaluation
+  float* ref_val;    // [cap]
+  int* ref_src;      // [cap]     their index in req_val
+  int* counters;     // [kNumCounters]  request counts per phase; the last four slots are fixed (see kCtr*)
+  int* ref_counters; // [kNumCounters]  prefilter: refined samples per 100-sample batch
   int R, N;
   long long cap;
   float thr, clip, line_step;
@@ -297,6 +305,96 @@ __global__ void sampler_select_kernel(TraceCtx c, const float* __restrict__ lin,
   c.s.flags[r] = fl;
 }
 
+// ------------------------------------------------------------------ prefilter of the 100-sample stages
+// req_val holds SCREENING values (error < tau / 2).  One thread per ray decides which samples the selection logic below
+// can possibly look at with more than their certain sign / certain non-minimality, and queues those for the exact kernel:
+//   * sign path (ray_sampler): with k = first certainly negative sample (v <= -tau) and j = first sample that is not
+//     certainly positive (v >= tau), the first negative sample lies in [j, k]; it and its predecessor (python's [-1]
+//     wrap for index 0) feed the secant -> refine [j-1, k].  Without a certainly negative sample: every uncertain sample
+//     and its predecessor;
+//   * arg-min path (P_out rays, rays without a negative sample, minimal_sdf_points): every sample within 2 tau of the
+//     screening minimum.
+// After the merge the selection kernels run unchanged; un-refined samples keep their screening values, of which only
+// the (certain) sign and the (certain) fact that they are not the minimum is used.
+__device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int li, const unsigned char* want) {
+  int n = 0;
+  for (int i = 0; i < kSteps; ++i) n += want[i];
+  if (n == 0) return;
+  int slot = atomicAdd(c.ref_counters + counter, n);
+  for (int i = 0; i < kSteps; ++i)
+    if (want[i]) {
+      const size_t src = (size_t)li * kSteps + i;
+      c.ref_pts[3 * (size_t)slot] = c.req_pts[3 * src];
+      c.ref_pts[3 * (size_t)slot + 1] = c.req_pts[3 * src + 1];
+      c.ref_pts[3 * (size_t)slot + 2] = c.req_pts[3 * src + 2];
+      c.ref_src[slot] = (int)src;
+      ++slot;
+    }
+}
+
+__global__ void prefilter_sampler_kernel(TraceCtx c, const uint8_t* __restrict__ obj_mask, float tau, int list_counter, int begin,
+                                         int batch, int counter) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= total) return;
+  const int r = c.s.list[begin + li];
+  const float* f = c.req_val + (size_t)li * kSteps;
+  unsigned char want[kSteps];
+  int k = -1, j = -1;
+  float fm = INFINITY;
+  for (int i = 0; i < kSteps; ++i) {
+    const float v = f[i];
+    want[i] = 0;
+    if (k < 0) {
+      if (!(v >= tau) && j < 0) j = i;          // (NaN counts as uncertain)
+      if (v <= -tau) k = i;
+    }
+    fm = fminf(fm, v);
+  }
+  if (k >= 0) {
+    for (int i = max(j - 1, 0); i <= k; ++i) want[i] = 1;
+    if (j == 0) want[kSteps - 1] = 1;
+  } else {
+    for (int i = 0; i < kSteps; ++i)
+      if (!(fabsf(f[i]) >= tau)) {
+        want[i] = 1;
+        want[i == 0 ? kSteps - 1 : i - 1] = 1;
+      }
+  }
+  const bool inside_true = obj_mask ? obj_mask[r] != 0 : true;
+  if (k < 0 || !inside_true) {
+    const float lim = fm + 2.f * tau;
+    for (int i = 0; i < kSteps; ++i)
+      if (!(f[i] >= lim)) want[i] = 1;
+  }
+  push_refine(c, counter, li, want);
+}
+
+__global__ void prefilter_argmin_kernel(TraceCtx c, float tau, int list_counter, int begin, int batch, int counter) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= total) return;
+  const float* f = c.req_val + (size_t)li * kSteps;
+  unsigned char want[kSteps];
+  float fm = INFINITY;
+  for (int i = 0; i < kSteps; ++i) fm = fminf(fm, f[i]);
+  const float lim = fm + 2.f * tau;
+  for (int i = 0; i < kSteps; ++i) want[i] = !(f[i] >= lim) ? 1 : 0;
+  push_refine(c, counter, li, want);
+}
+
+// exact values replace the screening values; kCtrViolations counts samples whose screening error exceeded tau / 2
+__global__ void prefilter_merge_kernel(TraceCtx c, float tau, int counter) {
+  const int n = c.ref_counters[counter];
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.counters[kCtrRefined] += n;      // launches of one stream: no race
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int src = c.ref_src[i];
+    const float exact = c.ref_val[i], lp = c.req_val[src];
+    if (!(fabsf(exact - lp) <= 0.5f * tau)) atomicAdd(c.counters + kCtrViolations, 1);
+    c.req_val[src] = exact;
+  }
+}
+
 // secant iterations (:260-278): `collect_prev` consumes f(z) of the previous request, `push` issues the next
 __global__ void secant_kernel(TraceCtx c, int list_counter, int collect_prev, int push, int counter) {
   const int total = c.counters[list_counter];
@@ -398,10 +496,10 @@ __global__ void trace_output_kernel(TraceCtx c, float* __restrict__ dists, uint8
   }
 }
 
-constexpr int kNumCounters = 256;
 
 struct WorkspaceLayout {
-  size_t off_counters, off_cam, off_f[9], off_i[4], off_flags, off_req_pts, off_req_val, total;
+  size_t off_counters, off_cam, off_f[9], off_i[4], off_flags, off_req_pts, off_req_val, off_ref_pts, off_ref_val, off_ref_src,
+      total;
   long long cap;
   int batch_rays;
 };
@@ -414,7 +512,7 @@ static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  w.off_counters = take(kNumCounters * 4);
+  w.off_counters = take(2 * kNumCounters * 4);
   w.off_cam = take((size_t)B * 3 * 4);
   for (int i = 0; i < 9; ++i) w.off_f[i] = take((size_t)R * 4);       // acc_s acc_e min max next_s next_e cur_s cur_e z
   for (int i = 0; i < 4; ++i) w.off_i[i] = take((size_t)R * 4);       // slot_s slot_e list list_pos
@@ -423,6 +521,9 @@ static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
   w.cap = std::max<long long>(2 * R, (long long)w.batch_rays * kSteps);
   w.off_req_pts = take((size_t)w.cap * 12);
   w.off_req_val = take((size_t)w.cap * 4);
+  w.off_ref_pts = take((size_t)w.cap * 12);      // prefilter: worst case every sample is refined
+  w.off_ref_val = take((size_t)w.cap * 4);
+  w.off_ref_src = take((size_t)w.cap * 4);
   w.total = off;
   return w;
 }
@@ -478,7 +579,11 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.cam = cam;
   c.req_pts = reinterpret_cast<float*>(ws + w.off_req_pts);
   c.req_val = reinterpret_cast<float*>(ws + w.off_req_val);
+  c.ref_pts = reinterpret_cast<float*>(ws + w.off_ref_pts);
+  c.ref_val = reinterpret_cast<float*>(ws + w.off_ref_val);
+  c.ref_src = reinterpret_cast<int*>(ws + w.off_ref_src);
   c.counters = reinterpret_cast<int*>(ws + w.off_counters);
+  c.ref_counters = c.counters + kNumCounters;
   c.R = (int)R;
   c.N = n_pixels;
   c.cap = w.cap;
@@ -486,13 +591,28 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.clip = prm->dist_clip;
   c.line_step = prm->line_search_step;
 
-  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, kNumCounters * 4, st), "memset counters");
+  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 2 * kNumCounters * 4, st), "memset counters");
   if (rc) return rc;
   const int grid_r = (int)((R + kBlock - 1) / kBlock);
   int ctr = 0;   // every request phase uses its own counter: no resets, no host round trips
   auto eval = [&](int counter) {
     return mlp_sdf(net, packed, c.req_pts, 0, c.counters + counter, MVSDF_HEAD_SDF_ONLY, c.req_val, nullptr, nullptr,
                    false, st);
+  };
+  // 100-sample stages with the prefilter: screening pass over all samples, exact pass over the undecidable ones
+  const float tau = prm->prefilter_tau;
+  int ref_ctr = 0;
+  auto eval_screened = [&](int counter, auto&& launch_select_candidates) {
+    if (ref_ctr >= kNumCounters) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many prefilter batches");
+    int e = mlp_sdf(net, packed, c.req_pts, 0, c.counters + counter, MVSDF_HEAD_SDF_ONLY, c.req_val, nullptr, nullptr, false, st,
+                    true);
+    if (e) return e;
+    launch_select_candidates(ref_ctr);
+    e = mlp_sdf(net, packed, c.ref_pts, 0, c.ref_counters + ref_ctr, MVSDF_HEAD_SDF_ONLY, c.ref_val, nullptr, nullptr, false, st);
+    if (e) return e;
+    note_launch(); prefilter_merge_kernel<<<sm_count() * 4, kBlock, 0, st>>>(c, tau, ref_ctr);
+    ++ref_ctr;
+    return (int)MVSDF_OK;
   };
   note_launch(); ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr);
   if ((rc = eval(ctr++))) return rc;
@@ -505,7 +625,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     }
   }
   note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr);
-  const int list_ctr = ctr++;
+  const int list_ctr = kCtrSamplerRays;
   note_launch(); trace_finish_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr);
   // sampler in batches of batch_rays rays (worst case: every ray unconverged)
   const int n_batches = (int)((R + w.batch_rays - 1) / w.batch_rays);
@@ -514,11 +634,19 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     const long long items = (long long)w.batch_rays * kSteps;
     note_launch(); sampler_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, linspace100, list_ctr, begin,
                                                                                 w.batch_rays, ctr);
-    if ((rc = eval(ctr))) return rc;
+    if (tau > 0.f) {
+      rc = eval_screened(ctr, [&](int rc_ctr) {
+        note_launch(); prefilter_sampler_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+            c, object_mask, tau, list_ctr, begin, w.batch_rays, rc_ctr);
+      });
+      if (rc) return rc;
+    } else if ((rc = eval(ctr))) {
+      return rc;
+    }
     note_launch(); sampler_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, linspace100, object_mask, training,
                                                                                    list_ctr, begin, w.batch_rays);
     ctr++;
-    if (ctr >= kNumCounters - 24) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many sampler batches");
+    if (ctr >= kCtrSamplerRays - 20) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many sampler batches");
   }
   for (int i = 0; i <= prm->n_secant_steps; ++i) {
     const int push = i < prm->n_secant_steps;
@@ -528,7 +656,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     }
   }
   if (training) {
-    const int ml_ctr = ctr++;
+    const int ml_ctr = kCtrMinSdfRays;
     note_launch(); minsdf_prepare_kernel<<<grid_r, kBlock, 0, st>>>(c, object_mask, ml_ctr);
     if (!prm->skip_min_sdf) {
       for (int b = 0; b < n_batches; ++b) {
@@ -536,11 +664,19 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
         const long long items = (long long)w.batch_rays * kSteps;
         note_launch(); minsdf_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
                                                                                    w.batch_rays, ctr);
-        if ((rc = eval(ctr))) return rc;
+        if (tau > 0.f) {
+          rc = eval_screened(ctr, [&](int rc_ctr) {
+            note_launch(); prefilter_argmin_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+                c, tau, ml_ctr, begin, w.batch_rays, rc_ctr);
+          });
+          if (rc) return rc;
+        } else if ((rc = eval(ctr))) {
+          return rc;
+        }
         note_launch(); minsdf_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
                                                                                       w.batch_rays);
         ctr++;
-        if (ctr >= kNumCounters - 2) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many min-sdf batches");
+        if (ctr >= kCtrSamplerRays) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many min-sdf batches");
       }
     }
   }

@@ -232,6 +232,9 @@ class RenderingNetwork(_PackedMlp):
         return ops.render_forward(self.packed(), points, view_dirs, normals, feature_vectors)
 
 
+DEFAULT_PREFILTER_TAU = 4.0e-3     # measured screening error: max 9.4e-4 (tools/diag_prefilter.py); the guard trips at tau/2
+
+
 class B200IDRNetwork(nn.Module):
     """Drop-in for IDRNetwork on the forward path (see module docstring)."""
 
@@ -253,6 +256,11 @@ class B200IDRNetwork(nn.Module):
         self.object_bounding_sphere = self.tracer_conf["object_bounding_sphere"]
         self.schedule = schedule if schedule is not None else default_schedule
         self.skip_min_sdf = False          # minimal_sdf_points feeds no MVSDF loss; keep for parity
+        # > 0: the tracer's 100-sample stages screen all samples with the single-product kernel and evaluate exactly
+        # only the samples the selection logic can depend on (include/mvsdf_b200.h, prefilter_tau); results are
+        # bit-identical to 0.0 (off) unless counters[255] (screening error > tau/2 seen) is non-zero
+        self.prefilter_tau = float(os.environ.get("MVSDF_PREFILTER_TAU", DEFAULT_PREFILTER_TAU))
+        self.prefilter_fallbacks = 0       # forwards repeated exactly because the screening guard tripped
         self._ws: Dict[str, torch.Tensor] = {}
         self.last_trace_counters: Optional[torch.Tensor] = None
 
@@ -279,6 +287,7 @@ class B200IDRNetwork(nn.Module):
         p.n_steps = c["n_steps"]
         p.n_secant_steps = c["n_secant_steps"]
         p.skip_min_sdf = 1 if self.skip_min_sdf else 0
+        p.prefilter_tau = self.prefilter_tau
         return p
 
     def trace(self, sdf_net, uv, pose, intrinsics, object_mask_u8, training: bool, steps01=None):
@@ -361,6 +370,22 @@ class B200IDRNetwork(nn.Module):
         with torch.no_grad():
             return self._forward_native(input, train_progress, steps01, eik_points, dsurf_rand)
 
+    def _screening_failed(self) -> bool:
+        """True when the tracer's prefilter saw a screening error above tau/2 (counter 255): its bit-exactness argument
+        needs error < tau, so the caller repeats the forward with the prefilter off.  Called right after a host
+        sync the forward needs anyway."""
+        if self.prefilter_tau <= 0.0 or self.last_trace_counters is None:
+            return False
+        return int(self.last_trace_counters[255].item()) != 0
+
+    def _redo_exact(self, fn, *args):
+        tau, self.prefilter_tau = self.prefilter_tau, 0.0
+        self.prefilter_fallbacks += 1
+        try:
+            return fn(*args)
+        finally:
+            self.prefilter_tau = tau
+
     def _phase0(self, train_progress) -> bool:
         conf = self.schedule
         flags = [conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
@@ -395,6 +420,8 @@ class B200IDRNetwork(nn.Module):
         surface_mask = network_object_mask & object_mask
         idx = surface_mask.nonzero(as_tuple=False).squeeze(1)            # data-dependent size: one host sync, as in the reference
         M = idx.shape[0]
+        if self._screening_failed():
+            return self._redo_exact(self._forward_autograd, input, train_progress, steps01, eik_points, dsurf_rand)
         x_s, t_s, d_s = points[idx], dists[idx].unsqueeze(-1), ray_dirs[idx]
         c_s = cam_loc.unsqueeze(1).expand(B, N, 3).reshape(-1, 3)[idx]
         sdf_p = [t for lin in self.implicit_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
@@ -491,6 +518,8 @@ class B200IDRNetwork(nn.Module):
                                       _lib.ptr(normals), _lib.ptr(surf_head), _lib.ptr(hit_index), _lib.ptr(hit_offsets),
                                       stream))
         M = int(hit_offsets[B].item())          # the single host sync: diff_surf_pts has a data-dependent shape
+        if self._screening_failed():
+            return self._redo_exact(self._forward_native, input, train_progress, steps01, eik_points, dsurf_rand)
         diff_surf_pts = surf_pts[:M]
         output = {
             "points": points,

@@ -11,6 +11,7 @@ from . import _lib
 
 HEAD_SDF_ONLY = 0
 HEAD_FULL = 1
+HEAD_SDF_SCREEN = 2     # SDF column at screening precision (the tracer's prefilter; include/mvsdf_b200.h)
 
 
 def _stream(device) -> c_void_p:
@@ -81,7 +82,7 @@ def sdf_forward(net: PackedNet, x: torch.Tensor, head: int = HEAD_FULL):
     """ImplicitNetwork.forward: [n,3] -> sdf [n] (HEAD_SDF_ONLY) or full [n, 2+F] (HEAD_FULL)."""
     x = _f32(x)
     n = x.shape[0]
-    if head == HEAD_SDF_ONLY:
+    if head in (HEAD_SDF_ONLY, HEAD_SDF_SCREEN):
         out = torch.empty(n, dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().mvsdf_sdf_forward(net.handle, _lib.ptr(net.blob), _lib.ptr(x), n, None, head,
                                                 _lib.ptr(out), None, _stream(x.device)))
