@@ -44,7 +44,9 @@ int mvsdf_abi_version(void);
 const char* mvsdf_last_error(void);
 /* Instrumentation (no reference counterpart): cumulative number of CUDA kernels this library has launched, and
  * optional CUDA-event timing of the MLP tile launches on their own stream (kinds: 0 SDF-only head, 1 full head,
- * 2 value+gradient, 3 rendering net).  mvsdf_profile_collect synchronises on the recorded events. */
+ * 2 value+gradient, 3 rendering net, 4 SDF-only head at screening precision; both arrays hold MVSDF_PROFILE_KINDS
+ * entries).  mvsdf_profile_collect synchronises on the recorded events. */
+#define MVSDF_PROFILE_KINDS 8
 long long mvsdf_launch_count(void);
 void mvsdf_profile_enable(int on);
 int mvsdf_profile_collect(float* ms_by_kind_host, int* launches_by_kind_host);

@@ -231,7 +231,7 @@ static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, b
   if (rc) return rc;
   const int max_pairs = sms / 2;
   const int n_pairs = device_count ? max_pairs : (int)std::min<long long>(pair_tiles, max_pairs);
-  const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : 0));
+  const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : ((kCanLp && a.lp) ? 4 : 0)));
   ProfEvent* pe = prof_begin(kind, st);
   note_launch();
   kern<<<2 * n_pairs, VER == 2 ? kP2Threads : kMlpThreads, smem, st>>>(a);
@@ -313,7 +313,7 @@ void mvsdf_profile_enable(int on) {
 }
 int mvsdf_profile_collect(float* ms_by_kind, int* launches_by_kind) {
   if (!ms_by_kind || !launches_by_kind) return fail(MVSDF_ERR_INVALID, "mvsdf_profile_collect: null argument");
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < MVSDF_PROFILE_KINDS; ++k) {
     ms_by_kind[k] = 0.f;
     launches_by_kind[k] = 0;
   }

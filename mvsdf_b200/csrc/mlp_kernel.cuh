@@ -150,6 +150,18 @@ __device__ __forceinline__ void pack_split_fh(float y0, float y1, uint32_t& hi2,
   asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo2) : "f"(l0), "f"(l1));
 }
 
+// screening-precision softplus: lg2(1 + e), e in (0, 1], as e * P4(e) (minimax, max error 1.6e-5 -- below the fp16 rounding
+// of the stored activation) instead of the second MUFU op: the SFU (8 cycles per warp instruction per SM sub-partition)
+// bounds the production epilogue at 16 cycles per element, this form is issue-bound at ~9.5 (tools/mufu_rate.cu)
+__device__ __forceinline__ float softplus_t_scaled_screen(float t) {
+  const float e = ptx::ex2_approx(-fabsf(t));
+  float p = fmaf(e, 0.044938717f, -0.19310565f);
+  p = fmaf(p, e, 0.41525051f);
+  p = fmaf(p, e, -0.70899308f);
+  p = fmaf(p, e, 1.4419080f);
+  return fmaf(p, e, fmaxf(t, 0.0f)) * kSpC;
+}
+
 // fp16 hi parts only (screening precision)
 __device__ __forceinline__ uint32_t pack_hi(float y0, float y1) {
   uint32_t h;

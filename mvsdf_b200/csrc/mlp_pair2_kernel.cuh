@@ -38,6 +38,13 @@ __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, 
 
 // debug timeline: slot = role * 16384 + index (role 0 issuer, 1 epilogue warp 0 of CTA 0, 2 epilogue warp 0 of CTA 1,
 // 3 producer of CTA 0)
+// bottleneck-isolation flags (MlpArgs::debug) exist in the diagnostic build only: in production they are the constant 0,
+// which removes a constant-bank load + branch from every epilogue element pair and every issuer stage
+#ifdef MVSDF_TRACE
+#define P2_DEBUG (a.debug)
+#else
+#define P2_DEBUG 0
+#endif
 #ifdef MVSDF_TRACE
 #define P2_TRACE(role, index)                                                                         \
   do {                                                                                                \
@@ -56,6 +63,9 @@ __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, 
 // (csrc/tracer.cu, prefilter); never for an output.
 template <int KIND, int MODE, int LP = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_pair2_kernel(const MlpArgs a) {
+  // K chunks per weight-ring stage.  LP: two hi tiles (K = 64) per stage -- at one N=256 UMMA per K step a 32-wide
+  // stage is 256 tensor cycles, less than the issuer thread's per-stage latency (~350 cycles)
+  constexpr int kChunksPerStage = LP ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,15 +131,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
           const int m = 2 * mp + (int)crank;
           const bool have = m < lp.m_tiles;
           const uint8_t* src = a.packed + lp.w_off + (size_t)m * lp.k_chunks * kStageBytes;
-          for (int kc = k0; kc < k1; ++kc, ++it) {
+          for (int kc = k0; kc < k1; kc += kChunksPerStage, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-            if (a.debug & 16) ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            if (P2_DEBUG & 16) ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
             else ptx::mbar_wait_sleep(bar_empty + 8 * s, ph ^ 1);
             if (lane == 0) {
-              if (have && !(a.debug & 1)) {
-                constexpr uint32_t kCopy = LP ? kTileBytes : kStageBytes;      // LP: the hi tile only
-                ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kCopy);
-                ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)kc * kStageBytes, kCopy, bar_full + 8 * s);
+              if (have && !(P2_DEBUG & 1)) {
+                if (LP) {       // the hi tiles of two consecutive K chunks share a stage (the second where lo would be)
+                  const int n_sub = min(2, k1 - kc);
+                  ptx::mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)n_sub * kTileBytes);
+                  for (int sub = 0; sub < n_sub; ++sub)
+                    ptx::bulk_g2s(s_stage + s * kStageBytes + sub * kTileBytes, src + (size_t)(kc + sub) * kStageBytes, kTileBytes,
+                                  bar_full + 8 * s);
+                } else {
+                  ptx::mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytes);
+                  ptx::bulk_g2s(s_stage + s * kStageBytes, src + (size_t)kc * kStageBytes, kStageBytes, bar_full + 8 * s);
+                }
               } else {
                 ptx::mbar_arrive(bar_full + 8 * s);     // odd tile count: this half multiplies stale data into rows nobody reads
               }
@@ -148,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     //  depend on which CTA processes it, and the outputs would no longer be bit-identical under re-sharding.)
     constexpr uint32_t idesc = ptx::idesc_f16_f32_bmn(2 * kTileM, LP ? 2 * kP2Cols : kP2Cols);
     const bool leader = ptx::elect_one();
-    const uint32_t issue = (leader && !(a.debug & 2)) ? 1u : 0u;
+    const uint32_t issue = (leader && !(P2_DEBUG & 2)) ? 1u : 0u;
     uint32_t it0 = 0, x_ctr = 0, d1_uses = 0;
     bool ready = false;      // the barrier of my next stage was already seen complete
     // shared-memory descriptors (ptx::smem_desc) as (low word, high word): only the 14-bit address field varies
@@ -198,9 +215,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
           const uint32_t d_a = tmem_base + (uint32_t)(mp * 2 * kP2Cols);
           const uint32_t d_b = d_a + kP2Cols;
           const uint32_t dlo_b = lp.b_from_pe ? dlo_pe : dlo_x;
-          const int n_st = k1 - k0;
+          const int n_st = (k1 - k0 + kChunksPerStage - 1) / kChunksPerStage;
           for (int j = 0; j < n_st; ++j) {
-            const int kc = k0 + j;
+            const int kc = k0 + j * kChunksPerStage;
             const uint32_t it = it0 + (uint32_t)j;
             const uint32_t st = it % kStages, ph = (it / kStages) & 1;
             if (!ready) ptx::mbar_wait(bar_full + 8 * st, ph);
@@ -210,14 +227,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
             ready = ptx::mbar_test_wait(bar_full + 8 * (itn % kStages), (itn / kStages) & 1);
             const uint32_t a_off = dlo_a + st * (kStageBytes >> 4);
             const uint32_t b_off = dlo_b + (uint32_t)kc * ((kChunkK / 8) * kBCoreStride >> 4);
+            if (LP) {
+              const int n_sub = min(2, k1 - kc);
 #pragma unroll
-            for (int ks = 0; ks < kChunkK / 16; ++ks) {
-              const uint64_t da_hi = ptx::desc_from_words(a_off + ks * (256 >> 4), dhi_a);
-              const uint64_t da_lo = ptx::desc_from_words(a_off + ((kTileBytes + ks * 256) >> 4), dhi_a);
-              const uint64_t db_hi = ptx::desc_from_words(b_off + ks * (2 * kBCoreStride >> 4), dhi_b);
-              const uint64_t db_lo = ptx::desc_from_words(b_off + ((kBLoOffset + ks * 2 * kBCoreStride) >> 4), dhi_b);
-              if (LP) ptx::umma1_f16_2cta(d_a, da_hi, db_hi, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
-              else ptx::umma3_f16_2cta(d_a, d_b, da_hi, da_lo, db_hi, db_lo, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
+              for (int sk = 0; sk < 2 * (kChunkK / 16); ++sk) {      // sk = 2 sub + ks: K steps of 16 over up to two chunks
+                if (sk < n_sub * (kChunkK / 16)) {
+                  const uint64_t da_hi = ptx::desc_from_words(a_off + (((sk >> 1) * kTileBytes + (sk & 1) * 256) >> 4), dhi_a);
+                  const uint64_t db_hi = ptx::desc_from_words(b_off + sk * (2 * kBCoreStride >> 4), dhi_b);
+                  ptx::umma1_f16_2cta(d_a, da_hi, db_hi, idesc, (kc | sk) != 0 ? 1u : 0u, issue);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < kChunkK / 16; ++ks) {
+                const uint64_t da_hi = ptx::desc_from_words(a_off + ks * (256 >> 4), dhi_a);
+                const uint64_t da_lo = ptx::desc_from_words(a_off + ((kTileBytes + ks * 256) >> 4), dhi_a);
+                const uint64_t db_hi = ptx::desc_from_words(b_off + ks * (2 * kBCoreStride >> 4), dhi_b);
+                const uint64_t db_lo = ptx::desc_from_words(b_off + ((kBLoOffset + ks * 2 * kBCoreStride) >> 4), dhi_b);
+                ptx::umma3_f16_2cta(d_a, d_b, da_hi, da_lo, db_hi, db_lo, idesc, (kc | ks) != 0 ? 1u : 0u, issue);
+              }
             }
             if (leader) ptx::umma_commit_2cta(bar_empty + 8 * st, 3);
             __syncwarp();
@@ -238,7 +266,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     for (long long g = pair0; g < n_tiles; g += pair_stride) {
       for (int l = 0; l < a.n_run; ++l) {
         const LayerPlan& lp = a.L[l];
-        const int n_stage = ((lp.m_tiles + 1) >> 1) * lp.k_chunks;
+        int n_stage = 0;
+        for (int part = 0; part < 4; ++part) {
+          int mp, k0, k1;
+          bool run;
+          p2_part(lp, part, mp, k0, k1, run);
+          if (run) n_stage += (k1 - k0 + kChunksPerStage - 1) / kChunksPerStage;
+        }
         for (int i = 0; i < n_stage; ++i, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           ptx::mbar_wait(bar_full + 8 * s, ph);
@@ -391,7 +425,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
         for (int mp = 0; mp < kP2Tiles; ++mp) {
           if (mp < n_pair_tiles) {
             if (tracer) P2_TRACE(1 + crank, tr + 4 * mp);          // waiting for D_mp
-            if (a.debug & 16) ptx::mbar_wait(bar_acc + 8 * mp, acc_ctr[mp] & 1);
+            if (P2_DEBUG & 16) ptx::mbar_wait(bar_acc + 8 * mp, acc_ctr[mp] & 1);
             else ptx::mbar_wait_sleep(bar_acc + 8 * mp, acc_ctr[mp] & 1);
             ++acc_ctr[mp];
             ptx::tc_fence_after();
@@ -440,14 +474,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                       const float ta1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, bias_k);
                       const float tb0 = fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k);
                       const float tb1 = fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k);
-                      phi[i] = pack_hi(softplus_t_scaled(ta0), softplus_t_scaled(ta1));
-                      plo[i] = pack_hi(softplus_t_scaled(tb0), softplus_t_scaled(tb1));
+                      phi[i] = pack_hi(softplus_t_scaled_screen(ta0), softplus_t_scaled_screen(ta1));
+                      plo[i] = pack_hi(softplus_t_scaled_screen(tb0), softplus_t_scaled_screen(tb1));
                       continue;
                     }
                     const float t0 = fmaf(__uint_as_float(va[hcol][2 * i]), kK, fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k));
                     const float t1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k));
-                    const float y0 = (KIND == NET_SDF && !(a.debug & 8)) ? softplus_t_scaled(t0) : fmaxf(t0, 0.0f);
-                    const float y1 = (KIND == NET_SDF && !(a.debug & 8)) ? softplus_t_scaled(t1) : fmaxf(t1, 0.0f);
+                    const float y0 = (KIND == NET_SDF && !(P2_DEBUG & 8)) ? softplus_t_scaled(t0) : fmaxf(t0, 0.0f);
+                    const float y1 = (KIND == NET_SDF && !(P2_DEBUG & 8)) ? softplus_t_scaled(t1) : fmaxf(t1, 0.0f);
                     pack_split_fh(y0, y1, phi[i], plo[i]);
                   }
                 } else {
@@ -474,7 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                       ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
                       ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
                     }
-                  } else if (!(a.debug & 4)) {
+                  } else if (!(P2_DEBUG & 4)) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       ptx::st_async_v4(dst_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3], dst_lx + 8 * mp);
@@ -546,7 +580,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                   const int pm = 2 * mp + (int)(crank ^ 1u);       // the peer's output tile: 256 B per row it writes
                   int rows = pm < lp.m_tiles ? kTileM : 0;
                   if (skip_src) rows = min(rows, max(a.skip_rows_begin - pm * kTileM, 0));
-                  if (rows > 0 && !(a.debug & 4)) ptx::mbar_arrive_expect_tx(bar_lx + 8 * mp, (uint32_t)rows * (kTileN * 4));
+                  if (rows > 0 && !(P2_DEBUG & 4)) ptx::mbar_arrive_expect_tx(bar_lx + 8 * mp, (uint32_t)rows * (kTileN * 4));
                   else ptx::mbar_arrive(bar_lx + 8 * mp);
                 } else {
                   ptx::mbar_arrive(bar_lx + 8 * mp);

@@ -14,13 +14,14 @@ sdf = ops.PackedNet("sdf", 512, 8).pack_state_dict(sd, "implicit_network", dev)
 n = 148 * 64 * 40
 xx = (torch.rand(n, 3, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(dev)
 L = _lib.lib()
-out = ops.sdf_forward(sdf, xx, ops.HEAD_SDF_ONLY)
+HEAD = ops.HEAD_SDF_SCREEN if os.environ.get('SCREEN', '0') == '1' else ops.HEAD_SDF_ONLY     # SCREEN=1: screening kernel
+out = ops.sdf_forward(sdf, xx, HEAD)
 torch.cuda.synchronize()
 buf = torch.zeros(4 * 16384, dtype=torch.int64, device=dev)
 L.mvsdf_debug_set_trace.argtypes = [ctypes.c_void_p]
 L.mvsdf_debug_set_trace.restype = None
 L.mvsdf_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
-out = ops.sdf_forward(sdf, xx, ops.HEAD_SDF_ONLY)
+out = ops.sdf_forward(sdf, xx, HEAD)
 torch.cuda.synchronize()
 L.mvsdf_debug_set_trace(ctypes.c_void_p(0))
 t = buf.cpu().view(4, 16384)
