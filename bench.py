@@ -57,6 +57,16 @@ def load_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(workload, tau):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01/dram_traffic_cfg2_v6.json:
+    dram__bytes_read.sum + dram__bytes_write.sum summed over the step's exact + screening SDF launches / their number).
+    It cannot be measured live; null for configurations that were not captured."""
+    p = os.path.join(ROOT, "profiles", "r01", "dram_traffic_cfg2_v6.json")
+    if workload != "cfg2" or abs(tau - 0.004) > 1e-9 or not os.path.exists(p):
+        return None
+    return json.load(open(p))["dram_bytes_per_launch"]
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -252,7 +262,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "mlp_pair2_kernel<NET_SDF, plain, SDF-only head> (exact + screening launches)",
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
+                         "traffic": ncu_traffic(args.workload, model.prefilter_tau),
                          "peak_source": peaks["source"] + " bf16_tflops_sustained",
                          "algorithmic_flops_per_launch": alg_flops_kernel / max(1, (n_kind[0] + n_kind[4]) / args.steps),
                          "launches_per_step": (n_kind[0] + n_kind[4]) / args.steps, "kernel_ms_per_step": ms_kernel,
