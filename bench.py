@@ -62,7 +62,7 @@ def ncu_traffic(workload, tau):
     dram__bytes_read.sum + dram__bytes_write.sum summed over the step's exact + screening SDF launches / their number).
     It cannot be measured live; null for configurations that were not captured."""
     p = os.path.join(ROOT, "profiles", "r01", "dram_traffic_cfg2_v6.json")
-    if workload != "cfg2" or abs(tau - 0.004) > 1e-9 or not os.path.exists(p):
+    if workload != "cfg2" or not (0.0 < tau <= 0.004) or not os.path.exists(p):
         return None
     return json.load(open(p))["dram_bytes_per_launch"]
 
@@ -278,7 +278,7 @@ def run_ours(args):
         }
         if cpu_base:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,7 +348,25 @@ def run_reference(args):
                 "times oracle/mvsdf_oracle.py, the restatement pinned to the unmodified reference by tests/golden and "
                 "tests/test_oracle.py, on all host cores",
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries print there while the bench runs (NCCL writes its version
+    banner to stdout, the oracle port prints like the reference does) is sent to stderr instead."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -363,6 +381,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -232,7 +232,7 @@ class RenderingNetwork(_PackedMlp):
         return ops.render_forward(self.packed(), points, view_dirs, normals, feature_vectors)
 
 
-DEFAULT_PREFILTER_TAU = 4.0e-3     # measured screening error: max 9.4e-4 (tools/diag_prefilter.py); the guard trips at tau/2
+DEFAULT_PREFILTER_TAU = 3.0e-3     # measured screening error: max 9.6e-4 (tools/diag_prefilter.py); the guard trips at tau/2
 
 
 class B200IDRNetwork(nn.Module):
