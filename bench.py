@@ -62,7 +62,7 @@ def ncu_traffic(workload, tau):
     dram__bytes_read.sum + dram__bytes_write.sum summed over the step's exact + screening SDF launches / their number).
     It cannot be measured live; null for configurations that were not captured."""
     p = os.path.join(ROOT, "profiles", "r01", "dram_traffic_cfg2_v6.json")
-    if workload != "cfg2" or not (0.0 < tau <= 0.004) or not os.path.exists(p):
+    if workload != "cfg2" or abs(tau - 0.003) > 1e-9 or not os.path.exists(p):
         return None
     return json.load(open(p))["dram_bytes_per_launch"]
 
@@ -240,6 +240,10 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(cfg, scene, sd, budget_s=args.cpu_budget)
+        try:
+            cpu_base["torch_cuda_port"] = torch_cuda_port_sample(cfg, scene, sd, dev)
+        except Exception as e:                      # a baseline, never a reason to lose the bench line
+            cpu_base["torch_cuda_port"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         line = {
@@ -317,6 +321,40 @@ def cpu_reference_sample(cfg, scene, sd, budget_s=20.0, threads=None):
             "sample": f"{n_done} rays (regular sub-grid of the {cfg['H']}x{cfg['W']} image, same weights/cameras/features), "
                       f"eval forward + feat loss + rgb L1 in {dt:.1f} s; oracle/mvsdf_oracle.py (PyTorch CPU restatement "
                       "pinned to the reference by tests/golden)"}
+
+
+def torch_cuda_port_sample(cfg, scene, sd, dev, n_sample=240000):
+    """Part of the baseline leg: the SAME oracle port, unchanged, with its tensors on cuda:0 -- i.e. the reference
+    algorithm as eager PyTorch-CUDA ops (fp32 cuBLAS SGEMMs, boolean-mask gathers, host syncs), which is what
+    BASELINE.json's north_star calls "the reference PyTorch-CUDA path".  Bounded sub-grid of the same workload."""
+    from oracle import mvsdf_oracle as O
+    N = scene["uv"].shape[1]
+    to = lambda d: {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    sw, rw = O.sdf_weights(sd).to(dev), O.render_weights(sd).to(dev)
+
+    def sub_scene(n):
+        stride = max(1, N // n)
+        idx = torch.arange(0, N, stride)[:n]
+        sub = dict(scene)
+        for k in ("uv", "object_mask", "rgb"):
+            sub[k] = scene[k][:, idx].contiguous()
+        return to(sub)
+
+    with torch.no_grad():
+        warm = sub_scene(4096)
+        O.hot_path_losses(O.idr_forward(sw, rw, warm, None, False), warm, 0.5)
+        sub = sub_scene(min(N, n_sample))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = O.idr_forward(sw, rw, sub, None, False)
+        ls = O.hot_path_losses(out, sub, 0.5)
+        float(ls["rgb_loss"])
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    n_done = sub["uv"].shape[0] * sub["uv"].shape[1]
+    return {"value": n_done / dt, "unit": "rays/s", "device": torch.cuda.get_device_name(dev),
+            "sample": f"{n_done} rays (regular sub-grid), eval forward + feat loss + rgb L1 in {dt:.2f} s; oracle port on cuda:0 "
+                      "(eager PyTorch fp32, TF32 off)"}
 
 
 def run_reference(args):
