@@ -166,6 +166,13 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
                              int n_images, int n_views, int h, int w, int channels, const float* size,
                              const float* center, double* partials, void* stream);
 int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_loss, void* stream);
+/* Backward of the same term w.r.t. the surface points (what autograd computes through F.grid_sample, the projections and
+ * the cosine similarity, loss.py:132-155; the feature maps are constants):  out_grad_pts [M,3] = upstream_grad[0] *
+ * d loss / d surf_pts, with partials [B,2] as left by mvsdf_feat_loss_partials (after the all-reduce in a multi-GPU run:
+ * the counts are the global denominators).  Every row of out_grad_pts is written (zeros where no term was kept). */
+int mvsdf_feat_loss_backward(const float* surf_pts, const int32_t* hit_offsets, const float* cams, const float* maps_nhwc,
+                             int n_images, int n_views, int h, int w, int channels, const float* size, const float* center,
+                             const double* partials, const float* upstream_grad, float* out_grad_pts, void* stream);
 
 /* ---- IDRLoss.get_depth_loss (code/model/loss.py:37-63) with carving_t2 + RunningTopK (code/utils/my_utils.py:168-201,
  * :269-331), use_invalid=False, smooth=None: for every eikonal point, the signed gap to the MVS depth surface along the

@@ -67,6 +67,8 @@ def _declare(lib):
     lib.mvsdf_feat_nchw_to_nhwc.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
     lib.mvsdf_feat_loss_partials.restype = c_int
     lib.mvsdf_feat_loss_partials.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
+    lib.mvsdf_feat_loss_backward.restype = c_int
+    lib.mvsdf_feat_loss_backward.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]
     lib.mvsdf_feat_loss_finalize.restype = c_int
     lib.mvsdf_feat_loss_finalize.argtypes = [P, c_int, P, P]
     lib.mvsdf_depth_loss_partials.restype = c_int

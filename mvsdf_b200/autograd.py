@@ -10,10 +10,11 @@ Forward values always come from libmvsdf_b200.so (the fused tcgen05 kernels).  W
                       (the reference gets them from ``create_graph=True``, :104).
 * ``RenderEval``   -- RenderingNetwork.forward (:145-167).
 * ``RgbL1`` / ``FeatConsistency`` / ``DepthL1`` -- IDRLoss.get_rgb_loss / get_feat_loss_corr / get_depth_loss
-                      (model/loss.py:21-28, :115-165, :37-63).  RgbL1 and DepthL1 have closed-form backwards.
+                      (model/loss.py:21-28, :115-165, :37-63).  RgbL1 and DepthL1 have closed-form backwards,
+                      FeatConsistency's backward is the native kernel mvsdf_feat_loss_backward.
 
-ROUND-1 STATUS OF THE BACKWARD: the backward passes below RE-COMPUTE the op with plain PyTorch ops (cuBLAS SGEMMs,
-``F.grid_sample``) inside ``backward`` and differentiate that -- a library path, not hand-written kernels.  It is only
+ROUND-1 STATUS OF THE BACKWARD: the backward passes of the two MLPs (``SdfEval``, ``RenderEval``) RE-COMPUTE the op with
+plain PyTorch ops (cuBLAS SGEMMs) inside ``backward`` and differentiate that -- a library path, not hand-written kernels.  It is only
 reached from ``loss.backward()``; nothing on the forward / inference path (the path BASELINE.json's metric measures) runs
 through it.  The fused tcgen05 backward (reverse sweep over the value+tangent columns, dW accumulation, Adam) is
 SURVEY.md section 8 row f1 and replaces the bodies of the ``backward`` methods without touching the interface.
@@ -192,23 +193,24 @@ def _feat_loss_torch(pts, hit_offsets: List[int], counts, feat, cam, feat_src, s
 
 
 class FeatConsistency(torch.autograd.Function):
-    """loss = FeatConsistency.apply(loss_module, pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn)."""
+    """loss = FeatConsistency.apply(loss_module, pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn).
+    Forward = mvsdf_feat_loss_partials / _finalize; backward = mvsdf_feat_loss_backward (native: projections, bilinear
+    tap derivatives and the cosine-similarity chain in one kernel).  ``_feat_loss_torch`` above is kept as the
+    differentiable statement the native backward is tested against (tests/test_gpu_autograd.py)."""
 
     @staticmethod
     def forward(ctx, module, pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn):
         out = module._feat_loss_native(pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn)
-        counts = module.last_partials["feat"][:, 1].clone()
-        ctx.save_for_backward(pts, hit_offsets, counts, feat, cam, feat_src, src_cams, size, center)
+        ctx.module = module
+        ctx.n_pts = pts.shape[0]
+        ctx.pts_shape = pts.shape
+        ctx.save_for_backward(module.last_partials["feat"], *module._feat_ctx)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        pts, hit_offsets, counts, feat, cam, feat_src, src_cams, size, center = ctx.saved_tensors
-        offs = [int(v) for v in hit_offsets.tolist()]
-        if offs[-1] == 0:
-            return None, torch.zeros_like(pts), None, None, None, None, None, None, None, None
-        with torch.enable_grad():
-            p_ = pts.detach().requires_grad_(True)
-            loss = _feat_loss_torch(p_, offs, counts, feat, cam, feat_src, src_cams, size, center)
-            gp, = torch.autograd.grad(loss, p_, g)
+        partial, *operands = ctx.saved_tensors
+        if ctx.n_pts == 0:
+            return None, g.new_zeros(ctx.pts_shape), None, None, None, None, None, None, None, None
+        gp = ctx.module._feat_loss_backward_native(operands, partial, g)
         return None, gp, None, None, None, None, None, None, None, None

@@ -266,6 +266,143 @@ __global__ void feat_loss_kernel(FeatArgs a) {
   if (cur_img >= 0 && lane == 0 && acc != 0.0) atomicAdd(a.partial + 2 * cur_img, acc);
 }
 
+// ---- backward of the feature-consistency term w.r.t. the surface points (row f1, first native piece) -----------------
+// d loss / d pts for loss = mean_i( sum_{v>=1, kept} |1 - corr_v| / count_i ): the feature maps are constants, so the
+// whole chain is  point -> (world2cam, cam2img: three eps-guarded divisions) -> pixel -> bilinear taps -> cosine
+// similarity.  One warp per surface point, lane = channel; the 2x3 Jacobian d(ix, iy)/d pts of a view is carried in
+// forward mode (identical in every lane), the channel sums are warp reductions.  Gradient flows through BOTH the
+// reference-view sample and the source-view sample, and only where the forward kept the term (in range in both views --
+// which also means the +-1.1 clamp is inactive -- and |1 - corr| < 0.5, loss.py:143-153).
+struct ViewSample {
+  float f, fx, fy;      // sampled channel value and its derivatives w.r.t. the pixel coordinates (ix, iy)
+  float J[2][3];        // d(ix, iy) / d pts
+  bool in;
+};
+
+__device__ __forceinline__ ViewSample project_and_sample(const float* __restrict__ cam, const float* __restrict__ map, int h, int w,
+                                                         float X, float Y, float Z, float half_size, int lane) {
+  ViewSample r;
+  float c[4], dc[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c[i] = dot4(cam + 4 * i, X, Y, Z, 1.f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dc[i][k] = cam[4 * i + k] * half_size;       // d(world)/d(pts) = size / 2
+  }
+  const float d0 = __fadd_rn(c[3], 1e-9f);
+  float cp[4], dcp[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    cp[i] = __fdiv_rn(c[i], d0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dcp[i][k] = (dc[i][k] - cp[i] * dc[3][k]) / d0;
+  }
+  const float d1 = __fadd_rn(cp[3], 1e-9f);
+  float x[3], dx[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    x[i] = __fdiv_rn(cp[i], d1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dx[i][k] = (dcp[i][k] - x[i] * dcp[3][k]) / d1;
+  }
+  const float* K = cam + 16;
+  float U[3], dU[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    U[j] = dot3(K + 4 * j, x[0], x[1], x[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dU[j][k] = K[4 * j] * dx[0][k] + K[4 * j + 1] * dx[1][k] + K[4 * j + 2] * dx[2][k];
+  }
+  const float d2 = __fadd_rn(U[2], 1e-9f);
+  const float u = __fdiv_rn(U[0], d2), vv = __fdiv_rn(U[1], d2);
+  float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fmul_rn(u, 0.5f), (float)w), 2.f), 1.f);
+  float gy = __fsub_rn(__fmul_rn(__fdiv_rn(__fmul_rn(vv, 0.5f), (float)h), 2.f), 1.f);
+  gx = fminf(fmaxf(gx, -1.1f), 1.1f);
+  gy = fminf(fmaxf(gy, -1.1f), 1.1f);
+  r.in = gx <= 1.f && gx >= -1.f && gy <= 1.f && gy >= -1.f;
+  // ix = ((gx + 1) w - 1) / 2 = u / 2 - 1/2  =>  d ix = d u / 2 (clamp inactive wherever the term is kept)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r.J[0][k] = 0.5f * (dU[0][k] - u * dU[2][k]) / d2;
+    r.J[1][k] = 0.5f * (dU[1][k] - vv * dU[2][k]) / d2;
+  }
+  const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w), 1.f), 0.5f);
+  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h), 1.f), 0.5f);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - x0f, wx0 = x0f + 1.f - ix, wy1 = iy - y0f, wy0 = y0f + 1.f - iy;
+  const bool xin0 = x0 >= 0 && x0 < w, xin1 = x1 >= 0 && x1 < w, yin0 = y0 >= 0 && y0 < h, yin1 = y1 >= 0 && y1 < h;
+  // zeros padding: an out-of-bounds tap contributes 0 to the value and to both derivatives (F.grid_sample backward)
+  const float t00 = (xin0 && yin0) ? __ldg(map + ((size_t)y0 * w + x0) * 32 + lane) : 0.f;
+  const float t01 = (xin1 && yin0) ? __ldg(map + ((size_t)y0 * w + x1) * 32 + lane) : 0.f;
+  const float t10 = (xin0 && yin1) ? __ldg(map + ((size_t)y1 * w + x0) * 32 + lane) : 0.f;
+  const float t11 = (xin1 && yin1) ? __ldg(map + ((size_t)y1 * w + x1) * 32 + lane) : 0.f;
+  r.f = t00 * wx0 * wy0 + t01 * wx1 * wy0 + t10 * wx0 * wy1 + t11 * wx1 * wy1;
+  r.fx = (t01 - t00) * wy0 + (t11 - t10) * wy1;
+  r.fy = (t10 - t00) * wx0 + (t11 - t01) * wx1;
+  return r;
+}
+
+struct FeatBwdArgs {
+  const float* pts;
+  const int* offsets;
+  const float* cams;
+  const float* maps;
+  const float* size;
+  const float* center;
+  const double* partial;   // [B,2]: the (global) counts (V-1) m_i are the denominators
+  const float* upstream;   // [1] d L / d loss
+  float* grad;             // [M,3]
+  int B, V, h, w;
+};
+
+__global__ void feat_loss_bwd_kernel(FeatBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int M = a.offsets[a.B];
+  const float size = a.size[0];
+  const float cx = a.center[0], cy = a.center[1], cz = a.center[2];
+  const float g_up = a.upstream[0];
+  int img = 0;
+  for (int p = warp_global; p < M; p += n_warps) {
+    while (img + 1 < a.B && p >= a.offsets[img + 1]) ++img;
+    const double cnt = a.partial[2 * img + 1];
+    const float scale = cnt > 0.0 ? g_up / ((float)cnt * (float)a.B) : 0.f;
+    const float X = __fadd_rn(__fmul_rn(__fmul_rn(a.pts[3 * (size_t)p], 0.5f), size), cx);
+    const float Y = __fadd_rn(__fmul_rn(__fmul_rn(a.pts[3 * (size_t)p + 1], 0.5f), size), cy);
+    const float Z = __fadd_rn(__fmul_rn(__fmul_rn(a.pts[3 * (size_t)p + 2], 0.5f), size), cz);
+    const size_t map_stride = (size_t)a.h * a.w * 32;
+    const ViewSample s0 = project_and_sample(a.cams + ((size_t)img * a.V) * 32, a.maps + ((size_t)img * a.V) * map_stride, a.h, a.w,
+                                             X, Y, Z, 0.5f * size, lane);
+    const float n0 = sqrtf(warp_sum(s0.f * s0.f));
+    const float N0 = fmaxf(n0, 1e-9f);
+    float g[3] = {0.f, 0.f, 0.f};
+    for (int v = 1; v < a.V; ++v) {
+      const ViewSample sv = project_and_sample(a.cams + ((size_t)img * a.V + v) * 32, a.maps + ((size_t)img * a.V + v) * map_stride,
+                                               a.h, a.w, X, Y, Z, 0.5f * size, lane);
+      const float nv = sqrtf(warp_sum(sv.f * sv.f));
+      const float Nv = fmaxf(nv, 1e-9f);
+      const float dt = warp_sum(s0.f * sv.f);
+      const float corr = __fdiv_rn(__fdiv_rn(dt, N0), Nv);
+      const float one_m = __fsub_rn(1.f, corr);
+      const float l = fabsf(one_m);
+      if (!(s0.in && sv.in && l < 0.5f)) continue;          // warp-uniform
+      const float sgn = one_m > 0.f ? -1.f : (one_m < 0.f ? 1.f : 0.f);      // d|1-c|/dc
+      const float inv = 1.f / (N0 * Nv);
+      // d corr / d f0[c], d corr / d fv[c]  (the norm clamps have zero derivative when active)
+      const float a0 = sv.f * inv - (n0 > 1e-9f ? corr * s0.f / (n0 * n0) : 0.f);
+      const float av = s0.f * inv - (nv > 1e-9f ? corr * sv.f / (nv * nv) : 0.f);
+      const float s0x = warp_sum(a0 * s0.fx), s0y = warp_sum(a0 * s0.fy);
+      const float svx = warp_sum(av * sv.fx), svy = warp_sum(av * sv.fy);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        g[k] += sgn * (s0.J[0][k] * s0x + s0.J[1][k] * s0y + sv.J[0][k] * svx + sv.J[1][k] * svy);
+    }
+    if (lane < 3) a.grad[3 * (size_t)p + lane] = scale * (lane == 0 ? g[0] : (lane == 1 ? g[1] : g[2]));
+  }
+}
+
 __global__ void feat_counts_kernel(const int* __restrict__ offsets, int B, int V, double* __restrict__ partial) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) partial[2 * b + 1] = (double)(offsets[b + 1] - offsets[b]) * (double)(V - 1);
@@ -575,6 +712,21 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
   note_launch(); feat_counts_kernel<<<(n_images + 63) / 64, 64, 0, st>>>(hit_offsets, n_images, n_views, partials);
   note_launch(); feat_loss_kernel<<<sms * 8, 256, 0, st>>>(a);
   return check_cuda(cudaGetLastError(), "feat_loss launch");
+}
+
+int mvsdf_feat_loss_backward(const float* surf_pts, const int32_t* hit_offsets, const float* cams, const float* maps_nhwc,
+                             int n_images, int n_views, int h, int w, int channels, const float* size, const float* center,
+                             const double* partials, const float* upstream_grad, float* out_grad_pts, void* stream) {
+  if (!surf_pts || !hit_offsets || !cams || !maps_nhwc || !size || !center || !partials || !upstream_grad || !out_grad_pts)
+    return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_backward: null argument");
+  if (channels != 32) return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_backward: 32 feature channels expected");
+  if (n_images <= 0 || n_views < 2 || h <= 0 || w <= 0) return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_backward: bad sizes");
+  const int sms = sm_count();
+  if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
+  FeatBwdArgs a{surf_pts, hit_offsets, cams, maps_nhwc, size, center, partials, upstream_grad, out_grad_pts,
+                n_images, n_views, h, w};
+  note_launch(); feat_loss_bwd_kernel<<<sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_cuda(cudaGetLastError(), "feat_loss_bwd launch");
 }
 
 int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_loss, void* stream) {

@@ -118,7 +118,23 @@ class B200IDRLoss(nn.Module):
             reduce_fn(partial)
         _lib.check(L.mvsdf_feat_loss_finalize(_lib.ptr(partial), B, _lib.ptr(out), stream))
         self.last_partials["feat"] = partial
+        self._feat_ctx = (pts, hit_offsets, cams, maps, size, center)      # operands of the native backward
         return out
+
+    @torch.no_grad()
+    def _feat_loss_backward_native(self, ctx_tensors, partial, upstream):
+        """d loss / d diff_surf_pts through mvsdf_feat_loss_backward (autograd of loss.py:132-155 in the reference)."""
+        pts, hit_offsets, cams, maps, size, center = ctx_tensors
+        L = _lib.lib()
+        dev = pts.device
+        B, V, h, w, C = maps.shape
+        grad = torch.empty_like(pts)
+        up = upstream.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.mvsdf_feat_loss_backward(_lib.ptr(pts), _lib.ptr(hit_offsets), _lib.ptr(cams), _lib.ptr(maps), B, V, h, w, C,
+                                              _lib.ptr(size), _lib.ptr(center), _lib.ptr(partial), _lib.ptr(up), _lib.ptr(grad),
+                                              stream))
+        return grad
 
     # ---- loss.py:37-63 (+ carving_t2 / RunningTopK, utils/my_utils.py:168-201, :269-331)
     def get_depth_loss(self, eikonal_points_hom, eikonal_output, depths, cams, size, center, far_thresh=None, far_att=None,

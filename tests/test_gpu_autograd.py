@@ -86,3 +86,47 @@ def test_no_grad_training_forward_keeps_native_path():
     assert (a["rgb_values"] - b["rgb_values"]).abs().max().item() < 1e-5
     assert (a["grad_theta"] - b["grad_theta"]).abs().max().item() < 1e-5
     assert (a["diff_surf_pts"] - b["diff_surf_pts"]).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("n_src,hw,seed", [(1, 32, 3), (4, 48, 8), (8, 40, 9)])
+def test_native_feat_loss_backward_vs_oracle_autograd(n_src, hw, seed):
+    """mvsdf_feat_loss_backward (d loss / d diff_surf_pts: projections with the eps-guarded divisions, bilinear tap
+    derivatives with zero padding, cosine similarity, the in-range / <0.5 masks) against PyTorch autograd through the
+    oracle's get_feat_loss_corr restatement, in fp64 so that the comparison is not limited by the reference's own rounding.
+    Points are random inside the unit ball: many project outside some views, some terms are dropped by the 0.5 gate."""
+    dev = torch.device("cuda:0")
+    B = 2
+    scene = synth.make_scene(hw, hw, n_images=B, n_src=n_src, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    counts = [137, 91]
+    pts = torch.randn(sum(counts), 3, generator=g)
+    pts = 0.6 * pts / pts.norm(dim=1, keepdim=True) * torch.rand(sum(counts), 1, generator=g) ** (1 / 3)
+    N = scene["uv"].shape[1]
+    mask = torch.zeros(B, N, dtype=torch.bool)
+    for i, c in enumerate(counts):
+        mask[i, :c] = True
+    mask = mask.reshape(-1)
+    # oracle, fp64 autograd
+    p64 = pts.double().requires_grad_(True)
+    ref = O.feat_loss_corr(p64, scene["feat"].double(), scene["cam"].double(), scene["feat_src"].double(),
+                           scene["src_cams"].double(), scene["size"][:1].double(), scene["center"][:1].double(), mask, mask)
+    ref = ref.sum() if ref.dim() else ref
+    (g_ref,) = torch.autograd.grad(ref * 3.0, p64)
+    # product path: forward + native backward through the autograd Function
+    loss_mod = B200IDRLoss()
+    pd = pts.to(dev).requires_grad_(True)
+    offs = torch.tensor([0, counts[0], sum(counts)], dtype=torch.int32, device=dev)
+    out = loss_mod.get_feat_loss_corr(pd, None, scene["feat"].to(dev), scene["cam"].to(dev), scene["feat_src"].to(dev),
+                                      scene["src_cams"].to(dev), scene["size"][:1].to(dev), scene["center"][:1].to(dev),
+                                      mask.to(dev), mask.to(dev), hit_offsets=offs)
+    assert abs(float(out) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    (out * 3.0).backward()
+    got = pd.grad.cpu().double()
+    scale = g_ref.abs().max().item()
+    assert scale > 0.0
+    row_err = (got - g_ref).abs().max(dim=1).values / scale
+    # a point exactly on a gate (in-range edge, |1-corr| = 0.5) may be kept in fp64 and dropped in fp32: allow one
+    bad = row_err > 2e-4
+    assert int(bad.sum()) <= 1, f"{int(bad.sum())} rows differ, worst {row_err.max().item():.3e}"
+    nz = (g_ref.abs().sum(dim=1) > 0)
+    assert int(((got.abs().sum(dim=1) > 0) != nz).sum()) <= 1, "kept / dropped terms differ from the oracle"
