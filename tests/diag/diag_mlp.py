@@ -1,6 +1,6 @@
 """Prints error statistics of the CUDA MLP kernels vs the fp64 oracle (diagnostic, not a test)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from mvsdf_b200 import ops, synth
 from oracle import mvsdf_oracle as O

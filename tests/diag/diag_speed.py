@@ -1,6 +1,6 @@
 """Times the SDF-only MLP kernel on a fixed batch (W=512). Env: MVSDF_CLUSTER, MVSDF_DEBUG_FLAGS, SCREEN=1 (screening kernel)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from mvsdf_b200 import ops, synth
 from oracle import mvsdf_oracle as O
