@@ -232,6 +232,7 @@ class RenderingNetwork(_PackedMlp):
         return ops.render_forward(self.packed(), points, view_dirs, normals, feature_vectors)
 
 
+PREFILTER_TAU_MAX = 2.5e-2
 DEFAULT_PREFILTER_TAU = 3.0e-3     # measured screening error: max 9.6e-4 (tools/diag_prefilter.py); the guard trips at tau/2
 
 
@@ -379,12 +380,16 @@ class B200IDRNetwork(nn.Module):
         return int(self.last_trace_counters[255].item()) != 0
 
     def _redo_exact(self, fn, *args):
-        tau, self.prefilter_tau = self.prefilter_tau, 0.0
+        """Repeats the forward with the prefilter off (exact by construction) and widens tau for the following calls:
+        the screening error depends on the weights, so a network that trips the guard once would trip it every step.
+        Past PREFILTER_TAU_MAX the refinement volume eats the gain and the prefilter is switched off."""
+        tau = self.prefilter_tau
+        self.prefilter_tau = 0.0
         self.prefilter_fallbacks += 1
         try:
             return fn(*args)
         finally:
-            self.prefilter_tau = tau
+            self.prefilter_tau = 2.0 * tau if 2.0 * tau <= PREFILTER_TAU_MAX else 0.0
 
     def _phase0(self, train_progress) -> bool:
         conf = self.schedule
