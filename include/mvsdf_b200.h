@@ -117,7 +117,8 @@ size_t mvsdf_trace_workspace_bytes(int64_t n_rays, int n_images);
  * RayTracing.forward (ray_tracing.py:27-98: sphere_tracing :101-196, ray_sampler :198-258, secant :260-278,
  * minimal_sdf_points :280-308) for n_images x n_pixels rays, with the SDF supplied as packed weights instead of
  * the Python closure of implicit_differentiable_renderer.py:194.
- *   uv [B,N,2] (x=col,y=row), pose [B,4,4] cam->world, intrinsics [B,4,4], object_mask [B*N] uint8 or NULL (= all ones);
+ *   uv [B,N,2] (x=col,y=row), pose [B,4,4] cam->world (the [B,7] quaternion form of rend_util.py:49-54 is expanded to
+ *   4x4 by the caller -- B200IDRNetwork does), intrinsics [B,4,4], object_mask [B*N] uint8 or NULL (= all ones);
  *   linspace100 [100] = torch.linspace(0,1,100) (ray_tracing.py:206); steps01 [100] ~ U(0,1) drawn by the caller from
  *   the CPU generator exactly like ray_tracing.py:287 (training only).
  * Outputs: out_ray_dirs [B*N,3], out_cam_loc [B,3] (optional), out_dists [B*N], out_net_mask [B*N] uint8

@@ -233,6 +233,21 @@ class RenderingNetwork(_PackedMlp):
 
 
 PREFILTER_TAU_MAX = 2.5e-2
+def _quaternion_pose(pose7: torch.Tensor) -> torch.Tensor:
+    """rend_util.get_camera_params :49-54: [B,7] = (quaternion r,i,j,k ; camera centre) -> cam->world [B,4,4].  O(B) host
+    glue in front of ray_setup_kernel; the value path only -- gradients w.r.t. trained cameras (train_cameras=True,
+    exp_runner.py:40 default False) are not produced."""
+    q = torch.nn.functional.normalize(pose7[:, :4].detach().to(torch.float32), dim=1)
+    r, i, j, k = q.unbind(dim=1)
+    R = torch.stack([1 - 2 * (j * j + k * k), 2 * (j * i - k * r), 2 * (i * k + r * j),
+                     2 * (j * i + k * r), 1 - 2 * (i * i + k * k), 2 * (j * k - i * r),
+                     2 * (k * i - j * r), 2 * (j * k + i * r), 1 - 2 * (i * i + j * j)], dim=1).view(-1, 3, 3)
+    p = torch.eye(4, dtype=torch.float32, device=pose7.device).repeat(pose7.shape[0], 1, 1)
+    p[:, :3, :3] = R
+    p[:, :3, 3] = pose7[:, 4:].detach().to(torch.float32)
+    return p.contiguous()
+
+
 DEFAULT_PREFILTER_TAU = 3.0e-3     # measured screening error: max 9.6e-4 (tools/diag_prefilter.py); the guard trips at tau/2
 
 
@@ -410,7 +425,7 @@ class B200IDRNetwork(nn.Module):
         uv, pose, intrinsics = ops._f32(input["uv"]), ops._f32(input["pose"]), ops._f32(input["intrinsics"])
         dev = uv.device
         if pose.shape[1] == 7:
-            raise NotImplementedError("quaternion poses (train_cameras=True) are outside the hot path")
+            pose = _quaternion_pose(pose)
         object_mask_true = input["object_mask"].reshape(-1).to(device=dev, dtype=torch.bool)
         object_mask = object_mask_true if conf.use_mask else torch.ones_like(object_mask_true)
         B, N, _ = uv.shape
@@ -490,7 +505,7 @@ class B200IDRNetwork(nn.Module):
         object_mask_true = input["object_mask"].reshape(-1).to(device=dev, dtype=torch.bool)
         object_mask = object_mask_true if conf.use_mask else torch.ones_like(object_mask_true)
         if pose.shape[1] == 7:
-            raise NotImplementedError("quaternion poses (train_cameras=True) are outside the hot path")
+            pose = _quaternion_pose(pose)
         B, N, _ = uv.shape
         R = B * N
         stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)

@@ -116,3 +116,25 @@ def test_training_forward_with_masked_pixels(skip_min_sdf):
         # `points` of non-hit rays come from minimal_sdf_points / closest approach (ray_tracing.py:73-94)
         if not skip_min_sdf:
             assert (out["points"].cpu() - ref["points"]).abs().max().item() < 2e-3
+
+
+def test_quaternion_pose_forward_equals_matrix_pose_forward():
+    """rend_util.get_camera_params accepts [B,7] poses (quaternion + centre, :49-54); so does the drop-in.  The 4x4 built
+    from the quaternion by the oracle must give the same outputs as passing the quaternion itself."""
+    from tests.test_oracle import _pose7_from_matrix
+    dev = torch.device("cuda:0")
+    sd = synth.make_state_dict(width=256, seed=1, perturb=0.05, pe_noise=0.003, bias=0.6)
+    model = _model(sd, 256, dev)
+    model.eval()
+    scene = synth.make_scene(20, 20, n_images=2, n_src=1, seed=6)
+    pose7 = _pose7_from_matrix(scene["pose"])
+    mat = O.quaternion_pose_matrix(pose7)
+    a = model({"uv": scene["uv"].to(dev), "pose": pose7.to(dev), "intrinsics": scene["intrinsics"].to(dev),
+               "object_mask": scene["object_mask"].to(dev)})
+    b = model({"uv": scene["uv"].to(dev), "pose": mat.to(dev), "intrinsics": scene["intrinsics"].to(dev),
+               "object_mask": scene["object_mask"].to(dev)})
+    assert int(a["network_object_mask"].sum()) > 0
+    hit = a["network_object_mask"] & b["network_object_mask"]
+    assert (a["network_object_mask"] != b["network_object_mask"]).float().mean().item() < 0.01
+    assert (a["points"][hit] - b["points"][hit]).abs().max().item() < 1e-4
+    assert (a["rgb_values"][hit] - b["rgb_values"][hit]).abs().max().item() < 2e-3

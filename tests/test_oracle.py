@@ -125,3 +125,28 @@ def test_live_reference_train_step_matches_oracle():
     (losses["rgb_loss"] + losses["feat_loss"] + losses["eikonal_loss"]).backward()
     for k, gr in ref_grads.items():
         assert torch.allclose(params[k].grad, gr, rtol=1e-3, atol=1e-6), k
+
+
+def _pose7_from_matrix(pose):
+    """Test helper: cam->world [B,4,4] -> [B,7] (quaternion r,i,j,k ; centre), valid for trace(R) > -1."""
+    R = pose[:, :3, :3].double()
+    qr = torch.sqrt(1.0 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]) / 2
+    q = torch.stack([qr, (R[:, 2, 1] - R[:, 1, 2]) / (4 * qr), (R[:, 0, 2] - R[:, 2, 0]) / (4 * qr),
+                     (R[:, 1, 0] - R[:, 0, 1]) / (4 * qr)], dim=1)
+    return torch.cat([q, pose[:, :3, 3].double()], dim=1).float()
+
+
+def test_quaternion_pose_is_the_matrix_pose():
+    """Row a1, quaternion branch (rend_util.py:49-54): a [B,7] pose gives the rays of the equivalent 4x4 pose."""
+    from mvsdf_b200 import synth
+    scene = synth.make_scene(12, 12, n_images=3, n_src=1, seed=4)
+    pose7 = _pose7_from_matrix(scene["pose"])
+    d7, c7 = O.camera_rays(scene["uv"], pose7, scene["intrinsics"])
+    d4, c4 = O.camera_rays(scene["uv"], scene["pose"], scene["intrinsics"])
+    assert torch.allclose(c7, c4, atol=1e-6) and torch.allclose(d7, d4, atol=2e-6)
+    if ref_shim.available():
+        ref = ref_shim.load()
+        rd, rc = ref.rend_util.get_camera_params(scene["uv"], pose7 * 1.7 * torch.tensor([1, 1, 1, 1, 1 / 1.7, 1 / 1.7, 1 / 1.7]),
+                                                 scene["intrinsics"])          # un-normalised quaternion: normalised inside
+        od, oc = O.camera_rays(scene["uv"], pose7 * 1.7 * torch.tensor([1, 1, 1, 1, 1 / 1.7, 1 / 1.7, 1 / 1.7]), scene["intrinsics"])
+        assert torch.allclose(od, rd, atol=1e-6) and torch.allclose(oc, rc, atol=1e-6)
