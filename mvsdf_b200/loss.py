@@ -1,7 +1,7 @@
 """Host-side mirror of IDRLoss for the terms on the north-star path (code/model/loss.py):
-get_rgb_loss (:21-28) and get_feat_loss_corr (:115-165) run in libmvsdf_b200.so; the eikonal
-and surface-indicator terms are tiny reductions on tensors the model already produced.
-The depth-carving term (:37-63, my_utils.carving_t2) is SURVEY.md section 8 row f2 (next)."""
+get_rgb_loss (:21-28), get_feat_loss_corr (:115-165, forward and backward) and the depth-carving term
+get_depth_loss (:37-63, my_utils.carving_t2) run in libmvsdf_b200.so; the eikonal and surface-indicator
+terms are tiny reductions on tensors the model already produced."""
 from __future__ import annotations
 
 from ctypes import c_void_p
