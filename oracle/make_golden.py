@@ -189,20 +189,31 @@ def case_tracer(ref, name, preset, H, W, n_images, training, seed):
 
 
 def main():
+    """python -m oracle.make_golden [case-name ...]   (no names: every case)"""
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = ref_shim.load()
     torch.set_num_threads(8)
-    case_mlp(ref, "mlp_w256", "w256", 192, seed=11)
-    case_mlp(ref, "mlp_w512", "w512", 128, seed=12)
-    case_tracer(ref, "tracer_eval_w256", "w256", 32, 32, 1, False, seed=0)
-    case_tracer(ref, "tracer_train_w256", "w256", 24, 24, 2, True, seed=1)
-    case_tracer(ref, "tracer_eval_w256_geo", "w256_geo", 24, 24, 1, False, seed=2)
-    # BASELINE.json configs[0]: 32x32 rays, 8x256 SDF MLP, 1 source view
-    case_forward(ref, "cfg1_eval_w256", "w256", 32, 32, 1, 1, None, False, None, seed=0)
-    case_forward(ref, "cfg1_train_w256", "w256", 32, 32, 2, 1, 512, True, 0.5, seed=0, mask_mode="disc")
-    case_forward(ref, "small_eval_w512", "w512", 20, 20, 1, 2, None, False, None, seed=3)
-    # phase 0 (train_progress < 1/6): depth-surface samples join the eikonal set (:226-251)
-    case_forward(ref, "train_phase0_w256", "w256", 64, 64, 2, 1, 256, True, 0.1, seed=5, mask_mode="disc")
+    cases = [
+        (case_mlp, ("mlp_w256", "w256", 192), dict(seed=11)),
+        (case_mlp, ("mlp_w512", "w512", 128), dict(seed=12)),
+        (case_tracer, ("tracer_eval_w256", "w256", 32, 32, 1, False), dict(seed=0)),
+        (case_tracer, ("tracer_train_w256", "w256", 24, 24, 2, True), dict(seed=1)),
+        (case_tracer, ("tracer_eval_w256_geo", "w256_geo", 24, 24, 1, False), dict(seed=2)),
+        # BASELINE.json configs[0]: 32x32 rays, 8x256 SDF MLP, 1 source view
+        (case_forward, ("cfg1_eval_w256", "w256", 32, 32, 1, 1, None, False, None), dict(seed=0)),
+        (case_forward, ("cfg1_train_w256", "w256", 32, 32, 2, 1, 512, True, 0.5), dict(seed=0, mask_mode="disc")),
+        (case_forward, ("small_eval_w512", "w512", 20, 20, 1, 2, None, False, None), dict(seed=3)),
+        # phase 0 (train_progress < 1/6): depth-surface samples join the eikonal set (:226-251)
+        (case_forward, ("train_phase0_w256", "w256", 64, 64, 2, 1, 256, True, 0.1), dict(seed=5, mask_mode="disc")),
+        # the shapes of BASELINE.json configs[1] / configs[2] at the headline width, ray counts the CPU reference finishes
+        # in seconds: eval with 4 source views; training (tp = 0.5) with 2 images x 8 source views
+        (case_forward, ("cfg2_shape_eval_w512", "w512", 28, 28, 1, 4, None, False, None), dict(seed=8)),
+        (case_forward, ("cfg3_shape_train_w512", "w512", 48, 48, 2, 8, 192, True, 0.5), dict(seed=9)),
+    ]
+    only = set(sys.argv[1:])
+    for fn, args, kw in cases:
+        if not only or args[0] in only:
+            fn(ref, *args, **kw)
 
 
 if __name__ == "__main__":

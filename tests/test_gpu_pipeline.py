@@ -46,7 +46,7 @@ def _check_forward(out, g, scene, training, max_flip_frac=0.01):
     return flips
 
 
-@pytest.mark.parametrize("name", ["cfg1_eval_w256", "small_eval_w512"])
+@pytest.mark.parametrize("name", ["cfg1_eval_w256", "small_eval_w512", "cfg2_shape_eval_w512"])
 def test_eval_forward_vs_reference_golden(golden, name):
     from mvsdf_b200.loss import B200IDRLoss
     g = golden(name)
@@ -67,9 +67,10 @@ def test_eval_forward_vs_reference_golden(golden, name):
         assert abs(float(losses["rgb_loss"]) - float(g["rgb_loss"])) < 0.02
 
 
-def test_train_forward_vs_reference_golden(golden):
+@pytest.mark.parametrize("name", ["cfg1_train_w256", "cfg3_shape_train_w512"])
+def test_train_forward_vs_reference_golden(golden, name):
     from mvsdf_b200.loss import B200IDRLoss
-    g = golden("cfg1_train_w256")
+    g = golden(name)
     dev = torch.device("cuda:0")
     model, sd = _model(str(g["meta_preset"]), dev)
     scene = scene_from_meta(g)

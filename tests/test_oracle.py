@@ -50,7 +50,8 @@ def test_tracer_golden(golden, name):
     assert cnt.total > 0
 
 
-@pytest.mark.parametrize("name", ["cfg1_eval_w256", "cfg1_train_w256", "small_eval_w512", "train_phase0_w256"])
+@pytest.mark.parametrize("name", ["cfg1_eval_w256", "cfg1_train_w256", "small_eval_w512", "train_phase0_w256",
+                                  "cfg2_shape_eval_w512", "cfg3_shape_train_w512"])
 def test_forward_golden(golden, name):
     g = golden(name)
     sd = preset_state_dict(str(g["meta_preset"]), g["meta_weights_sha"])
