@@ -42,6 +42,13 @@ WORKLOADS = {
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
     "cfg1": dict(H=32, W=32, width=256, n_src=1, n_images=1, n_rays=None, training=False,
                  weights=dict(width=256, seed=1, perturb=0.05, pe_noise=0.003, bias=0.6)),
+    # BASELINE.json configs[3]: ONE 1.2 M-ray image sharded across the ranks as contiguous ray ranges (strong scaling):
+    # every rank holds the whole feature maps, the loss partials are all-reduced
+    "cfg4": dict(H=1200, W=1600, width=512, n_src=4, n_images=1, n_rays=1200000, training=False, shard_rays=True,
+                 weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
+    # configs[4]: Tanks&Temples-shaped 1080p, 12 source views; one image per rank (weak scaling)
+    "cfg5": dict(H=1080, W=1920, width=512, n_src=12, n_images=1, n_rays=None, training=False,
+                 weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
 }
 
 # algorithmic FLOPs per SDF evaluation / shaded ray
@@ -101,10 +108,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def make_inputs(cfg, rank):
-    """Host (pinned) tensors of one step. Every rank renders a different view of the same synthetic scene."""
+def make_inputs(cfg, rank, world=1):
+    """Host tensors of one step.  Weak-scaling workloads: every rank renders a different view of the same synthetic
+    scene.  shard_rays workloads: all ranks hold the SAME image and rank r takes the r-th contiguous range of its rays
+    (contiguous ray ranges within an image, maps replicated)."""
+    shard = bool(cfg.get("shard_rays"))
     scene = synth.make_scene(cfg["H"], cfg["W"], n_images=cfg["n_images"], n_src=cfg["n_src"], n_rays=cfg["n_rays"],
-                             seed=rank)
+                             seed=0 if shard else rank)
+    if shard and world > 1:
+        from mvsdf_b200 import parallel
+        scene = parallel.shard_rays(scene, rank, world)
     sd = synth.make_state_dict(**cfg["weights"])
     return scene, sd
 
@@ -132,7 +145,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = WORKLOADS[args.workload]
-    scene, sd = make_inputs(cfg, rank)
+    scene, sd = make_inputs(cfg, rank, world)
     B, N = scene["uv"].shape[:2]
     R = B * N
     model = B200IDRNetwork(default_conf(cfg["width"])).to(dev)
@@ -248,12 +261,15 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if cfg.get("shard_rays") else "weak",
+            "vs_baseline": None,
             "dtype": "fp32-equivalent (fp16 hi/lo split operands, fp32 tensor-core accumulate)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg['H']}x{cfg['W']} image, {R} rays/GPU, {cfg['n_src']} src views, "
                                    f"8x{width} SDF MLP + 4x{width} render MLP, {'train' if cfg['training'] else 'eval'}-mode forward "
                                    f"+ feat loss + rgb L1", "rays_per_gpu": R, "hit_fraction": n_hit / R,
-                       "tracer_evals_per_ray": evals / R, "parallelism": f"ray-sharded dp{world}, loss-partials all-reduce",
+                       "tracer_evals_per_ray": evals / R,
+                       "parallelism": (f"one image, contiguous ray ranges over {world} ranks" if cfg.get("shard_rays") else
+                                       f"one image per rank, dp{world}") + ", loss-partials all-reduce",
                        "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
                        "skip_min_sdf": bool(args.skip_min_sdf),
                        "prefilter": {"tau": model.prefilter_tau, "refined_evals_per_ray": refined / R,
