@@ -474,6 +474,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                       const float ta1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, bias_k);
                       const float tb0 = fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k);
                       const float tb1 = fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k);
+                      if (P2_DEBUG & 8) {      // diagnostic build only: ReLU instead of softplus (epilogue issue load / 3)
+                        phi[i] = pack_hi(fmaxf(ta0, 0.f), fmaxf(ta1, 0.f));
+                        plo[i] = pack_hi(fmaxf(tb0, 0.f), fmaxf(tb1, 0.f));
+                        continue;
+                      }
                       phi[i] = pack_hi(softplus_t_scaled_screen(ta0), softplus_t_scaled_screen(ta1));
                       plo[i] = pack_hi(softplus_t_scaled_screen(tb0), softplus_t_scaled_screen(tb1));
                       continue;
@@ -504,7 +509,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                 if (write) {
                   if (hcol == 1) {
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
+                    for (int j = 0; j < 2 && !(P2_DEBUG & 32); ++j) {      // bit 5 (diagnostic build): skip the local stores
                       ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
                       ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
                     }
