@@ -211,8 +211,8 @@ def run_ours(args):
 
     # tracer evaluations of the last step (E_trace of SURVEY 8d: requests the reference algorithm issues)
     cnt = model.last_trace_counters.cpu()
-    evals = int(cnt[:252].sum().item())                          # include/mvsdf_b200.h: MVSDF_CTR_*
-    refined, violations = int(cnt[254]), int(cnt[255])
+    evals = int(cnt[:251].sum().item())                          # include/mvsdf_b200.h: MVSDF_CTR_*
+    screened, refined, violations = int(cnt[251]), int(cnt[254]), int(cnt[255])
     n_hit = int(out["hit_offsets"][-1].item())
     width = cfg["width"]
     fl = FLOP[width]
@@ -272,10 +272,11 @@ def run_ours(args):
                                        f"one image per rank, dp{world}") + ", loss-partials all-reduce",
                        "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
                        "skip_min_sdf": bool(args.skip_min_sdf),
-                       "prefilter": {"tau": model.prefilter_tau, "refined_evals_per_ray": refined / R,
+                       "prefilter": {"tau": model.prefilter_tau, "screened_evals_per_ray": screened / R, "refined_evals_per_ray": refined / R,
                                      "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
-                                     "note": "100-sample stages: screening pass (1 fp16 product) over all samples + exact "
-                                             "pass (3 products) over the undecidable ones; outputs bit-identical to tau=0"}},
+                                     "note": "100-sample stages: screening pass (1 fp16 product, chunks of 20 samples, stops behind "
+                                             "the first certainly negative sample) + exact pass (3 products) over the undecidable "
+                                             "samples; outputs bit-identical to tau=0"}},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes},

@@ -97,15 +97,18 @@ typedef struct mvsdf_tracer_params {
   int skip_min_sdf;       /* training only: drop minimal_sdf_points (:280-308), whose outputs no MVSDF loss reads */
   float prefilter_tau;    /* 0 = off.  > 0: the 100-sample stages (ray_sampler :206-235, minimal_sdf_points :287-305) first
                              evaluate all samples at screening precision and re-evaluate exactly only the samples whose sign
-                             (|sdf| < tau), secant end points or arg-min rank the screening value cannot decide.  Results
+                             (|sdf| < tau), secant end points or arg-min rank the screening value cannot decide; the
+                             screening pass of ray_sampler walks the samples in chunks and stops at the first chunk with a
+                             certainly negative sample (nothing behind it is read by :221-249).  Results
                              are bit-identical to tau = 0 as long as the screening error stays below tau; out_counters
                              [MVSDF_CTR_VIOLATIONS] counts refined samples whose screening error exceeded tau / 2 -- a
                              caller that sees it non-zero repeats the call with tau = 0 (B200IDRNetwork does). */
 } mvsdf_tracer_params;
 
 #define MVSDF_NUM_TRACE_COUNTERS 256
-/* out_counters: slots [0, MVSDF_CTR_SAMPLER_RAYS) are the SDF evaluations the reference algorithm requests per phase (their
+/* out_counters: slots [0, MVSDF_CTR_SCREENED) are the SDF evaluations the reference algorithm requests per phase (their
  * sum is E_trace of SURVEY 8d, independent of the prefilter); the fixed slots: */
+#define MVSDF_CTR_SCREENED 251       /* prefilter: samples evaluated at screening precision (the chunked pass stops early) */
 #define MVSDF_CTR_SAMPLER_RAYS 252   /* rays that entered ray_sampler (ray_tracing.py:44-61) */
 #define MVSDF_CTR_MINSDF_RAYS 253    /* rays that entered minimal_sdf_points (:86-94), training only */
 #define MVSDF_CTR_REFINED 254        /* prefilter: samples evaluated a second time at full precision */

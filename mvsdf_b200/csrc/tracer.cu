@@ -57,8 +57,8 @@ struct RayState {
 };
 
 constexpr int kNumCounters = 256;
-// fixed slots of out_counters (include/mvsdf_b200.h): everything below kCtrSamplerRays is an SDF request count
-constexpr int kCtrSamplerRays = 252, kCtrMinSdfRays = 253, kCtrRefined = 254, kCtrViolations = 255;
+// fixed slots of out_counters (include/mvsdf_b200.h): everything below kCtrScreened is an SDF request count
+constexpr int kCtrScreened = 251, kCtrSamplerRays = 252, kCtrMinSdfRays = 253, kCtrRefined = 254, kCtrViolations = 255;
 
 struct TraceCtx {
   RayState s;
@@ -70,6 +70,8 @@ struct TraceCtx {
   int* ref_src;      // [cap]     their index in req_val
   int* counters;     // [kNumCounters]  request counts per phase; the last four slots are fixed (see kCtr*)
   int* ref_counters; // [kNumCounters]  prefilter: refined samples per 100-sample batch
+  int* pf_counts;    // [kNumCounters]  prefilter: per (batch, sample chunk) active rays / points of the chunked screening pass
+  int* act_list[2];  // [batch_rays]    rays of the batch that still need their next sample chunk (ping-pong)
   int R, N;
   long long cap;
   float thr, clip, line_step;
@@ -254,6 +256,7 @@ __global__ void sampler_push_kernel(TraceCtx c, const float* __restrict__ lin, i
   c.req_pts[3 * (size_t)idx] = p.x;
   c.req_pts[3 * (size_t)idx + 1] = p.y;
   c.req_pts[3 * (size_t)idx + 2] = p.z;
+  c.req_val[idx] = INFINITY;      // chunked screening: a sample that is never evaluated reads as "certainly positive, not the minimum"
 }
 
 // first sign change / arg-min selection and secant initialisation (:221-256); one thread per sampler ray
@@ -332,6 +335,54 @@ __device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int 
     }
 }
 
+// ---- chunked screening pass of ray_sampler's 100 samples --------------------------------------------------------------
+// The selection reads nothing beyond the first certainly negative sample k of a ray whose pixel is inside the true mask
+// (first sign change <= k; the arg-min is only taken for P_out rays, :230-235).  The screening pass therefore walks the
+// samples in chunks of kChunk and drops a ray from the following chunks as soon as a chunk contains a value <= -tau;
+// samples never evaluated keep +inf, which every consumer treats as "certainly positive and not the minimum".  Rays
+// outside the true mask (training) and rays without a certain negative sample see all chunks.
+constexpr int kChunk = 20;
+constexpr int kNumChunks = kSteps / kChunk;
+
+// points of chunk `chunk` of the active rays -> compact list (ref_pts, ref_src); act == nullptr: every ray of the batch
+__global__ void chunk_gather_kernel(TraceCtx c, const int* __restrict__ act, const int* __restrict__ n_act_ptr, int list_counter,
+                                    int begin, int batch, int chunk, int* __restrict__ n_pts_out) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  const int n_act = act ? *n_act_ptr : total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *n_pts_out = n_act * kChunk;
+    c.counters[kCtrScreened] += n_act * kChunk;      // launches of one stream: no race
+  }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_act * kChunk) return;
+  const int a = idx / kChunk, i = chunk * kChunk + (idx - a * kChunk);
+  const int li = act ? act[a] : a;
+  const size_t src = (size_t)li * kSteps + i;
+  c.ref_pts[3 * (size_t)idx] = c.req_pts[3 * src];
+  c.ref_pts[3 * (size_t)idx + 1] = c.req_pts[3 * src + 1];
+  c.ref_pts[3 * (size_t)idx + 2] = c.req_pts[3 * src + 2];
+}
+
+// screening values of the chunk -> req_val; rays that still need the next chunk -> act_next
+__global__ void chunk_decide_kernel(TraceCtx c, const uint8_t* __restrict__ obj_mask, float tau, const int* __restrict__ act,
+                                    const int* __restrict__ n_act_ptr, int list_counter, int begin, int batch, int chunk,
+                                    int* __restrict__ act_next, int* __restrict__ n_act_next) {
+  const int total = min(max(c.counters[list_counter] - begin, 0), batch);
+  const int n_act = act ? *n_act_ptr : total;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_act) return;
+  const int li = act ? act[a] : a;
+  const int r = c.s.list[begin + li];
+  const bool inside_true = obj_mask ? obj_mask[r] != 0 : true;
+  bool found = false;
+  for (int i = 0; i < kChunk; ++i) {
+    const float v = c.ref_val[(size_t)a * kChunk + i];
+    c.req_val[(size_t)li * kSteps + chunk * kChunk + i] = v;
+    if (v <= -tau) found = true;
+  }
+  if (act_next && !(found && inside_true)) act_next[atomicAdd(n_act_next, 1)] = li;
+}
+
 __global__ void prefilter_sampler_kernel(TraceCtx c, const uint8_t* __restrict__ obj_mask, float tau, int list_counter, int begin,
                                          int batch, int counter) {
   const int total = min(max(c.counters[list_counter] - begin, 0), batch);
@@ -373,6 +424,7 @@ __global__ void prefilter_sampler_kernel(TraceCtx c, const uint8_t* __restrict__
 __global__ void prefilter_argmin_kernel(TraceCtx c, float tau, int list_counter, int begin, int batch, int counter) {
   const int total = min(max(c.counters[list_counter] - begin, 0), batch);
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li == 0) c.counters[kCtrScreened] += total * kSteps;
   if (li >= total) return;
   const float* f = c.req_val + (size_t)li * kSteps;
   unsigned char want[kSteps];
@@ -390,7 +442,7 @@ __global__ void prefilter_merge_kernel(TraceCtx c, float tau, int counter) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int src = c.ref_src[i];
     const float exact = c.ref_val[i], lp = c.req_val[src];
-    if (!(fabsf(exact - lp) <= 0.5f * tau)) atomicAdd(c.counters + kCtrViolations, 1);
+    if (lp != INFINITY && !(fabsf(exact - lp) <= 0.5f * tau)) atomicAdd(c.counters + kCtrViolations, 1);   // +inf: never screened
     c.req_val[src] = exact;
   }
 }
@@ -499,7 +551,7 @@ __global__ void trace_output_kernel(TraceCtx c, float* __restrict__ dists, uint8
 
 struct WorkspaceLayout {
   size_t off_counters, off_cam, off_f[9], off_i[4], off_flags, off_req_pts, off_req_val, off_ref_pts, off_ref_val, off_ref_src,
-      total;
+      off_act[2], total;
   long long cap;
   int batch_rays;
 };
@@ -512,7 +564,7 @@ static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  w.off_counters = take(2 * kNumCounters * 4);
+  w.off_counters = take(3 * kNumCounters * 4);
   w.off_cam = take((size_t)B * 3 * 4);
   for (int i = 0; i < 9; ++i) w.off_f[i] = take((size_t)R * 4);       // acc_s acc_e min max next_s next_e cur_s cur_e z
   for (int i = 0; i < 4; ++i) w.off_i[i] = take((size_t)R * 4);       // slot_s slot_e list list_pos
@@ -524,6 +576,7 @@ static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
   w.off_ref_pts = take((size_t)w.cap * 12);      // prefilter: worst case every sample is refined
   w.off_ref_val = take((size_t)w.cap * 4);
   w.off_ref_src = take((size_t)w.cap * 4);
+  for (int i = 0; i < 2; ++i) w.off_act[i] = take((size_t)w.batch_rays * 4);
   w.total = off;
   return w;
 }
@@ -584,6 +637,8 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.ref_src = reinterpret_cast<int*>(ws + w.off_ref_src);
   c.counters = reinterpret_cast<int*>(ws + w.off_counters);
   c.ref_counters = c.counters + kNumCounters;
+  c.pf_counts = c.counters + 2 * kNumCounters;
+  for (int i = 0; i < 2; ++i) c.act_list[i] = reinterpret_cast<int*>(ws + w.off_act[i]);
   c.R = (int)R;
   c.N = n_pixels;
   c.cap = w.cap;
@@ -591,7 +646,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.clip = prm->dist_clip;
   c.line_step = prm->line_search_step;
 
-  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 2 * kNumCounters * 4, st), "memset counters");
+  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 3 * kNumCounters * 4, st), "memset counters");
   if (rc) return rc;
   const int grid_r = (int)((R + kBlock - 1) / kBlock);
   int ctr = 0;   // every request phase uses its own counter: no resets, no host round trips
@@ -635,18 +690,34 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     note_launch(); sampler_push_kernel<<<(int)((items + kBlock - 1) / kBlock), kBlock, 0, st>>>(c, linspace100, list_ctr, begin,
                                                                                 w.batch_rays, ctr);
     if (tau > 0.f) {
-      rc = eval_screened(ctr, [&](int rc_ctr) {
-        note_launch(); prefilter_sampler_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(
-            c, object_mask, tau, list_ctr, begin, w.batch_rays, rc_ctr);
-      });
-      if (rc) return rc;
+      // chunked screening pass (see chunk_gather_kernel), then the exact pass over the undecidable samples
+      if ((b + 1) * kNumChunks * 2 > kNumCounters || ref_ctr >= kNumCounters)
+        return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many prefilter batches");
+      const int chunk_grid = (int)(((long long)w.batch_rays * kChunk + kBlock - 1) / kBlock);
+      for (int ch = 0; ch < kNumChunks; ++ch) {
+        int* cnt = c.pf_counts + (b * kNumChunks + ch) * 2;             // [0] active rays of this chunk, [1] its points
+        const int* act = ch == 0 ? nullptr : c.act_list[ch & 1];
+        int* act_next = ch + 1 < kNumChunks ? c.act_list[(ch + 1) & 1] : nullptr;
+        note_launch(); chunk_gather_kernel<<<chunk_grid, kBlock, 0, st>>>(c, act, cnt, list_ctr, begin, w.batch_rays, ch, cnt + 1);
+        if ((rc = mlp_sdf(net, packed, c.ref_pts, 0, cnt + 1, MVSDF_HEAD_SDF_ONLY, c.ref_val, nullptr, nullptr, false, st, true)))
+          return rc;
+        note_launch(); chunk_decide_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+            c, object_mask, tau, act, cnt, list_ctr, begin, w.batch_rays, ch, act_next, cnt + 2);
+      }
+      note_launch(); prefilter_sampler_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+          c, object_mask, tau, list_ctr, begin, w.batch_rays, ref_ctr);
+      if ((rc = mlp_sdf(net, packed, c.ref_pts, 0, c.ref_counters + ref_ctr, MVSDF_HEAD_SDF_ONLY, c.ref_val, nullptr, nullptr, false,
+                        st)))
+        return rc;
+      note_launch(); prefilter_merge_kernel<<<sm_count() * 4, kBlock, 0, st>>>(c, tau, ref_ctr);
+      ++ref_ctr;
     } else if ((rc = eval(ctr))) {
       return rc;
     }
     note_launch(); sampler_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, linspace100, object_mask, training,
                                                                                    list_ctr, begin, w.batch_rays);
     ctr++;
-    if (ctr >= kCtrSamplerRays - 20) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many sampler batches");
+    if (ctr >= kCtrScreened - 20) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many sampler batches");
   }
   for (int i = 0; i <= prm->n_secant_steps; ++i) {
     const int push = i < prm->n_secant_steps;
@@ -676,7 +747,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
         note_launch(); minsdf_select_kernel<<<(w.batch_rays + kBlock - 1) / kBlock, kBlock, 0, st>>>(c, steps01, ml_ctr, begin,
                                                                                       w.batch_rays);
         ctr++;
-        if (ctr >= kCtrSamplerRays) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many min-sdf batches");
+        if (ctr >= kCtrScreened) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many min-sdf batches");
       }
     }
   }

@@ -38,6 +38,21 @@ def candidates_sampler(lp, tau, inside_true):
     return want
 
 
+CHUNK = 20
+
+
+def chunked_screening(lp, tau, inside_true):
+    """chunk_gather_kernel / chunk_decide_kernel: the screening pass walks the samples in chunks of CHUNK and stops after
+    the first chunk that holds a value <= -tau when the pixel is inside the true mask; what was never evaluated is +inf."""
+    seen = np.full(S, np.inf, dtype=np.float32)
+    for c in range(S // CHUNK):
+        sl = slice(c * CHUNK, (c + 1) * CHUNK)
+        seen[sl] = lp[sl]
+        if inside_true and (lp[sl] <= -tau).any():
+            break
+    return seen
+
+
 def candidates_argmin(lp, tau):
     """prefilter_argmin_kernel."""
     return ~(lp >= lp.min() + 2.0 * tau)
@@ -97,6 +112,11 @@ def test_sampler_rule_never_changes_the_selection(tau, noise):
             want = candidates_sampler(lp[r], np.float32(tau), inside_true)
             merged = np.where(want, f[r], lp[r])
             assert select_sampler(merged, inside_true, training) == select_sampler(f[r], inside_true, training), (r, noise)
+            # same with the chunked screening pass: samples behind the deciding chunk are never evaluated (+inf)
+            seen = chunked_screening(lp[r], np.float32(tau), inside_true)
+            want = candidates_sampler(seen, np.float32(tau), inside_true)
+            merged = np.where(want, f[r], seen)
+            assert select_sampler(merged, inside_true, training) == select_sampler(f[r], inside_true, training), (r, noise, "chunked")
 
 
 @pytest.mark.parametrize("tau", [3e-3, 1e-3])

@@ -64,6 +64,6 @@ for (preset, H, W, training) in [("w256", 96, 96, False), ("w256", 96, 96, True)
         else:
             eq = lambda a, b: bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all()) if a.is_floating_point() else bool((a == b).all())
             same = f"dists {eq(dists, base[0])} mask {eq(nm, base[1])} points {eq(pts, base[2])} (max |d dists| {(dists - base[0]).abs().nan_to_num().max().item():.2e})"
-        print(f"{preset} {H}x{W} train={training} tau={tau:g}: {ms:.2f} ms, evals/ray {int(cnt[:252].sum()) / R:.1f}, "
+        print(f"{preset} {H}x{W} train={training} tau={tau:g}: {ms:.2f} ms, evals/ray {int(cnt[:251].sum()) / R:.1f}, screened/ray {int(cnt[251]) / R:.1f}, "
               f"sampler rays {int(cnt[252]) / R:.3f}, minsdf rays {int(cnt[253]) / R:.3f}, refined/ray {int(cnt[254]) / R:.2f}, "
               f"violations {int(cnt[255])}; bit-identical: {same}")
