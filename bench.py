@@ -65,11 +65,11 @@ def load_peaks():
 
 
 def ncu_traffic(workload, tau):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01/dram_traffic_cfg2_v6.json:
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01/dram_traffic_cfg2_v7.json:
     dram__bytes_read.sum + dram__bytes_write.sum summed over the step's exact + screening SDF launches / their number).
     It cannot be measured live; null for configurations that were not captured."""
-    p = os.path.join(ROOT, "profiles", "r01", "dram_traffic_cfg2_v6.json")
-    if workload != "cfg2" or abs(tau - 0.003) > 1e-9 or not os.path.exists(p):
+    p = os.path.join(ROOT, "profiles", "r01", "dram_traffic_cfg2_v7.json")
+    if workload != "cfg2" or abs(tau - 0.002) > 1e-9 or not os.path.exists(p):
         return None
     return json.load(open(p))["dram_bytes_per_launch"]
 
@@ -274,7 +274,7 @@ def run_ours(args):
                        "skip_min_sdf": bool(args.skip_min_sdf),
                        "prefilter": {"tau": model.prefilter_tau, "screened_evals_per_ray": screened / R, "refined_evals_per_ray": refined / R,
                                      "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
-                                     "note": "100-sample stages: screening pass (1 fp16 product, chunks of 20 samples, stops behind "
+                                     "note": "100-sample stages: screening pass (1 fp16 product, 5 chunks of 10-30 samples, stops behind "
                                              "the first certainly negative sample) + exact pass (3 products) over the undecidable "
                                              "samples; outputs bit-identical to tau=0"}},
             "clocks": clk,

@@ -338,24 +338,27 @@ __device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int 
 // ---- chunked screening pass of ray_sampler's 100 samples --------------------------------------------------------------
 // The selection reads nothing beyond the first certainly negative sample k of a ray whose pixel is inside the true mask
 // (first sign change <= k; the arg-min is only taken for P_out rays, :230-235).  The screening pass therefore walks the
-// samples in chunks of kChunk and drops a ray from the following chunks as soon as a chunk contains a value <= -tau;
+// samples in chunks (chunk_begin) and drops a ray from the following chunks as soon as a chunk contains a value <= -tau;
 // samples never evaluated keep +inf, which every consumer treats as "certainly positive and not the minimum".  Rays
 // outside the true mask (training) and rays without a certain negative sample see all chunks.
-constexpr int kChunk = 20;
-constexpr int kNumChunks = kSteps / kChunk;
+constexpr int kNumChunks = 5;
+// chunk boundaries: sphere tracing leaves acc_start just in front of the surface, so most crossings sit in the first samples
+__host__ __device__ constexpr int chunk_begin(int c) { return c == 0 ? 0 : c == 1 ? 10 : c == 2 ? 20 : c == 3 ? 40 : c == 4 ? 70 : kSteps; }
+constexpr int kChunkMax = 30;
 
 // points of chunk `chunk` of the active rays -> compact list (ref_pts, ref_src); act == nullptr: every ray of the batch
 __global__ void chunk_gather_kernel(TraceCtx c, const int* __restrict__ act, const int* __restrict__ n_act_ptr, int list_counter,
                                     int begin, int batch, int chunk, int* __restrict__ n_pts_out) {
   const int total = min(max(c.counters[list_counter] - begin, 0), batch);
   const int n_act = act ? *n_act_ptr : total;
+  const int c0 = chunk_begin(chunk), len = chunk_begin(chunk + 1) - c0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *n_pts_out = n_act * kChunk;
-    c.counters[kCtrScreened] += n_act * kChunk;      // launches of one stream: no race
+    *n_pts_out = n_act * len;
+    c.counters[kCtrScreened] += n_act * len;      // launches of one stream: no race
   }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_act * kChunk) return;
-  const int a = idx / kChunk, i = chunk * kChunk + (idx - a * kChunk);
+  if (idx >= n_act * len) return;
+  const int a = idx / len, i = c0 + (idx - a * len);
   const int li = act ? act[a] : a;
   const size_t src = (size_t)li * kSteps + i;
   c.ref_pts[3 * (size_t)idx] = c.req_pts[3 * src];
@@ -375,9 +378,10 @@ __global__ void chunk_decide_kernel(TraceCtx c, const uint8_t* __restrict__ obj_
   const int r = c.s.list[begin + li];
   const bool inside_true = obj_mask ? obj_mask[r] != 0 : true;
   bool found = false;
-  for (int i = 0; i < kChunk; ++i) {
-    const float v = c.ref_val[(size_t)a * kChunk + i];
-    c.req_val[(size_t)li * kSteps + chunk * kChunk + i] = v;
+  const int c0 = chunk_begin(chunk), len = chunk_begin(chunk + 1) - c0;
+  for (int i = 0; i < len; ++i) {
+    const float v = c.ref_val[(size_t)a * len + i];
+    c.req_val[(size_t)li * kSteps + c0 + i] = v;
     if (v <= -tau) found = true;
   }
   if (act_next && !(found && inside_true)) act_next[atomicAdd(n_act_next, 1)] = li;
@@ -693,7 +697,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
       // chunked screening pass (see chunk_gather_kernel), then the exact pass over the undecidable samples
       if ((b + 1) * kNumChunks * 2 > kNumCounters || ref_ctr >= kNumCounters)
         return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many prefilter batches");
-      const int chunk_grid = (int)(((long long)w.batch_rays * kChunk + kBlock - 1) / kBlock);
+      const int chunk_grid = (int)(((long long)w.batch_rays * kChunkMax + kBlock - 1) / kBlock);
       for (int ch = 0; ch < kNumChunks; ++ch) {
         int* cnt = c.pf_counts + (b * kNumChunks + ch) * 2;             // [0] active rays of this chunk, [1] its points
         const int* act = ch == 0 ? nullptr : c.act_list[ch & 1];

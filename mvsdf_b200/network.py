@@ -248,7 +248,7 @@ def _quaternion_pose(pose7: torch.Tensor) -> torch.Tensor:
     return p.contiguous()
 
 
-DEFAULT_PREFILTER_TAU = 3.0e-3     # measured screening error: max 9.6e-4 (tools/diag_prefilter.py); the guard trips at tau/2
+DEFAULT_PREFILTER_TAU = 2.0e-3     # screening error (tools/diag_prefilter.py): max 9.6e-4 over the unit cube, 4e-4 near the surface; the guard trips at tau/2
 
 
 class B200IDRNetwork(nn.Module):

@@ -38,15 +38,15 @@ def candidates_sampler(lp, tau, inside_true):
     return want
 
 
-CHUNK = 20
+CHUNKS = (0, 10, 20, 40, 70, 100)        # chunk_begin() of csrc/tracer.cu
 
 
 def chunked_screening(lp, tau, inside_true):
-    """chunk_gather_kernel / chunk_decide_kernel: the screening pass walks the samples in chunks of CHUNK and stops after
-    the first chunk that holds a value <= -tau when the pixel is inside the true mask; what was never evaluated is +inf."""
+    """chunk_gather_kernel / chunk_decide_kernel: the screening pass walks the samples in chunks and stops after the
+    first chunk that holds a value <= -tau when the pixel is inside the true mask; what was never evaluated is +inf."""
     seen = np.full(S, np.inf, dtype=np.float32)
-    for c in range(S // CHUNK):
-        sl = slice(c * CHUNK, (c + 1) * CHUNK)
+    for c in range(len(CHUNKS) - 1):
+        sl = slice(CHUNKS[c], CHUNKS[c + 1])
         seen[sl] = lp[sl]
         if inside_true and (lp[sl] <= -tau).any():
             break
