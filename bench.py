@@ -211,8 +211,8 @@ def run_ours(args):
 
     # tracer evaluations of the last step (E_trace of SURVEY 8d: requests the reference algorithm issues)
     cnt = model.last_trace_counters.cpu()
-    evals = int(cnt[:251].sum().item())                          # include/mvsdf_b200.h: MVSDF_CTR_*
-    screened, refined, violations = int(cnt[251]), int(cnt[254]), int(cnt[255])
+    evals = int(cnt[:_lib.CTR_SCREENED].sum().item())             # include/mvsdf_b200.h: MVSDF_CTR_*
+    screened, refined, violations = int(cnt[_lib.CTR_SCREENED]), int(cnt[_lib.CTR_REFINED]), int(cnt[_lib.CTR_VIOLATIONS])
     n_hit = int(out["hit_offsets"][-1].item())
     width = cfg["width"]
     fl = FLOP[width]

@@ -14,6 +14,10 @@ LIB_PATH = os.environ.get("MVSDF_LIB_PATH") or os.path.join(_HERE, "libmvsdf_b20
 
 _lib = None
 
+# fixed slots of mvsdf_trace's out_counters (include/mvsdf_b200.h, MVSDF_CTR_*); slots below CTR_SCREENED sum to E_trace
+CTR_SCREENED, CTR_SAMPLER_RAYS, CTR_MINSDF_RAYS, CTR_REFINED, CTR_VIOLATIONS = 251, 252, 253, 254, 255
+PROFILE_KINDS = 8
+
 
 class MvsdfError(RuntimeError):
     pass

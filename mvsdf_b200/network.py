@@ -392,7 +392,7 @@ class B200IDRNetwork(nn.Module):
         sync the forward needs anyway."""
         if self.prefilter_tau <= 0.0 or self.last_trace_counters is None:
             return False
-        return int(self.last_trace_counters[255].item()) != 0
+        return int(self.last_trace_counters[_lib.CTR_VIOLATIONS].item()) != 0
 
     def _redo_exact(self, fn, *args):
         """Repeats the forward with the prefilter off (exact by construction) and widens tau for the following calls:

@@ -65,3 +65,23 @@ def test_no_cpu_fallback(lib):
     net = ops.PackedNet("sdf", 256, 8)
     rc = lib.mvsdf_sdf_forward(net.handle, ctypes.c_void_p(16), ctypes.c_void_p(16), 4, None, 0, ctypes.c_void_p(16), None, None)
     assert rc < 0 and b"no CUDA device" in lib.mvsdf_last_error()
+
+
+def test_python_constants_match_the_header():
+    """The ctypes side indexes out_counters / the profile arrays with literals; they must be the header's."""
+    from mvsdf_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mvsdf_b200.h")).read()
+    macro = lambda name: int(re.search(r"#define\s+" + name + r"\s+(\d+)", hdr).group(1))
+    assert _lib.CTR_SCREENED == macro("MVSDF_CTR_SCREENED")
+    assert _lib.CTR_SAMPLER_RAYS == macro("MVSDF_CTR_SAMPLER_RAYS")
+    assert _lib.CTR_MINSDF_RAYS == macro("MVSDF_CTR_MINSDF_RAYS")
+    assert _lib.CTR_REFINED == macro("MVSDF_CTR_REFINED")
+    assert _lib.CTR_VIOLATIONS == macro("MVSDF_CTR_VIOLATIONS")
+    assert _lib.PROFILE_KINDS == macro("MVSDF_PROFILE_KINDS")
+    assert macro("MVSDF_NUM_TRACE_COUNTERS") == 256
+    # the tracer parameter block: same field order and size as the C struct (10 x 4 bytes)
+    fields = [f for f, _ in _lib.lib().TracerParams._fields_]
+    c_fields = re.search(r"typedef struct mvsdf_tracer_params \{(.*?)\} mvsdf_tracer_params;", hdr, re.S).group(1)
+    c_names = re.findall(r"^\s*(?:float|int)\s+(\w+);", c_fields, re.M)
+    assert fields == c_names, (fields, c_names)
+    assert ctypes.sizeof(_lib.lib().TracerParams) == 4 * len(c_names)
