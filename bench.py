@@ -220,6 +220,15 @@ def run_ours(args):
     alg_flops_kernel = sdf_only_evals * fl["sdf_only"]            # per step, kernel kind 0
     ms_kernel = (ms_kind[0] + ms_kind[4]) / args.steps          # exact + screening launches of the SDF-only kernel
     peaks = load_peaks()
+    # what the kernels actually executed (the prefilter proves most sampler evaluations irrelevant and skips them):
+    # exact evaluations = requests outside the 100-sample stages + refined samples + sdf_output; 3 fp16 products each
+    sampled = 100 * (int(cnt[_lib.CTR_SAMPLER_RAYS]) + (int(cnt[_lib.CTR_MINSDF_RAYS]) if cfg["training"] and not args.skip_min_sdf else 0))
+    if model.prefilter_tau > 0:
+        exact_exec = evals - sampled + refined + R
+        screen_exec = screened
+    else:
+        exact_exec, screen_exec = evals + R, 0
+    exec_tflop = (3 * exact_exec + screen_exec) * fl["sdf_only"] / 1e12
     achieved = alg_flops_kernel / (ms_kernel * 1e-3) / 1e12 if ms_kernel > 0 else None
     total_alg_flops = evals * fl["sdf_only"] + R * fl["sdf_only"] + n_hit * (3 * fl["full"] + fl["render"])
     if cfg["training"]:
@@ -289,6 +298,11 @@ def run_ours(args):
                          "algorithmic_flops_per_launch": alg_flops_kernel / max(1, (n_kind[0] + n_kind[4]) / args.steps),
                          "launches_per_step": (n_kind[0] + n_kind[4]) / args.steps, "kernel_ms_per_step": ms_kernel,
                          "kernel_share_of_step": ms_kernel / ms_per_step,
+                         "executed": {"exact_evals_per_ray": exact_exec / R, "screening_evals_per_ray": screen_exec / R,
+                                      "fp16_tensor_tflops": exec_tflop / (ms_kernel * 1e-3) if ms_kernel > 0 else None,
+                                      "frac_of_peak": (exec_tflop / (ms_kernel * 1e-3) / peaks["bf16_sustained"]) if ms_kernel > 0 else None,
+                                      "note": "fp16 tensor FLOPs the two kernels really issued (3 products per exact MAC, 1 per "
+                                              "screening MAC) over the same launch time"},
                          "note": "algorithmic FLOPs = 2*MAC of the fp32 network x the SDF evaluations the REFERENCE algorithm "
                                  "requests (E_trace + R, prefilter-independent); an exact evaluation issues 3 fp16 UMMAs per "
                                  "MAC (hi*hi + lo*hi + hi*lo), a screening evaluation 1, a refined sample 1 + 3"},

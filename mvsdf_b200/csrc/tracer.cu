@@ -659,7 +659,10 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
                    false, st);
   };
   // 100-sample stages with the prefilter: screening pass over all samples, exact pass over the undecidable ones
-  const float tau = prm->prefilter_tau;
+  // the prefilter keeps two device counters per (sampler batch, sample chunk); beyond that many batches (R > 6.5 M rays
+  // per call) the call simply runs without it -- same results, by construction
+  const int n_batches_pf = (int)((R + w.batch_rays - 1) / w.batch_rays);
+  const float tau = (n_batches_pf * kNumChunks * 2 > kNumCounters) ? 0.f : prm->prefilter_tau;
   int ref_ctr = 0;
   auto eval_screened = [&](int counter, auto&& launch_select_candidates) {
     if (ref_ctr >= kNumCounters) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: too many prefilter batches");
