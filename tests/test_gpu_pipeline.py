@@ -173,8 +173,20 @@ def test_tracer_vs_reference_golden(golden, name):
     d_ref = t(g["dists"])
     rel = ((dists.cpu() - d_ref).abs() / d_ref.abs().clamp_min(1e-6))[both]
     assert (rel > DEPTH_RTOL).float().mean().item() <= 0.01, rel.max().item()
+    # E_trace (the numerator of bench.py's roofline): the request counters must be the evaluation count of the REFERENCE
+    # algorithm -- here the oracle's counter on the same rays -- whatever the prefilter skips or repeats
+    from mvsdf_b200 import _lib
     cnt = model.last_trace_counters.cpu()
-    assert int(cnt.sum()) > 0
+    e_trace = int(cnt[:_lib.CTR_SCREENED].sum())
+    oc = O.TraceCounters()
+    o_dirs, o_cam = O.camera_rays(scene["uv"], scene["pose"], scene["intrinsics"])
+    sw = O.sdf_weights(sd)
+    with torch.no_grad():
+        O.trace_rays(lambda x: O.sdf_mlp(x, sw)[:, 0], o_cam, scene["object_mask"].reshape(-1), o_dirs, training=training,
+                     steps01=steps, counters=oc)
+    assert abs(e_trace - oc.total) <= 0.01 * oc.total, (e_trace, oc.total)
+    if model.prefilter_tau > 0:
+        assert int(cnt[_lib.CTR_SCREENED]) + int(cnt[_lib.CTR_REFINED]) < oc.sampler + oc.min_sdf or oc.sampler + oc.min_sdf == 0
 
 
 def test_shard_invariance_of_loss_partials():
