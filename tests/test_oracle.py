@@ -151,3 +151,39 @@ def test_quaternion_pose_is_the_matrix_pose():
                                                  scene["intrinsics"])          # un-normalised quaternion: normalised inside
         od, oc = O.camera_rays(scene["uv"], pose7 * 1.7 * torch.tensor([1, 1, 1, 1, 1 / 1.7, 1 / 1.7, 1 / 1.7]), scene["intrinsics"])
         assert torch.allclose(od, rd, atol=1e-6) and torch.allclose(oc, rc, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("training", [False, True])
+def test_e_trace_counts_are_the_reference_tracers_own_evaluations(training):
+    """bench.py's roofline counts algorithmic FLOPs as E_trace x FLOPs per SDF evaluation.  E_trace
+    must be what the REFERENCE tracer evaluates: run the unmodified RayTracing.forward with a counting SDF closure and
+    compare with the oracle's TraceCounters on the same rays (the GPU test then ties the kernels' counters to the oracle)."""
+    ref = ref_shim.load()
+    from mvsdf_b200 import synth
+    sd = preset_state_dict("w256")
+    sw = O.sdf_weights(sd)
+    scene = synth.make_scene(20, 20, n_images=2, n_src=1, seed=4, mask_mode="disc" if training else "ones")
+    dirs, cam = O.camera_rays(scene["uv"], scene["pose"], scene["intrinsics"])
+    rt_conf = ref_shim.model_conf(256)["ray_tracer"]
+    tracer = ref.ray_tracing.RayTracing(**rt_conf)
+    tracer.train(training)
+    n_evals = [0]
+
+    def counting_sdf(x):
+        n_evals[0] += x.shape[0]
+        return O.sdf_mlp(x, sw)[:, 0]
+
+    torch.manual_seed(3)
+    with torch.no_grad(), ref_shim.quiet():
+        r_pts, r_mask, r_dists = tracer(sdf=counting_sdf, cam_loc=cam, object_mask=scene["object_mask"].reshape(-1),
+                                        ray_directions=dirs)
+    torch.manual_seed(3)
+    oc = O.TraceCounters()
+    with torch.no_grad():
+        o_pts, o_mask, o_dists = O.trace_rays(lambda x: O.sdf_mlp(x, sw)[:, 0], cam, scene["object_mask"].reshape(-1), dirs,
+                                              training=training, counters=oc)
+    assert torch.equal(o_mask, r_mask)
+    assert torch.allclose(o_dists, r_dists, rtol=1e-6, atol=1e-6)
+    # the reference evaluates the 100 sampler points of EVERY ray slot it gathered, in 100 000-point chunks: same count
+    assert oc.total == n_evals[0], (oc, n_evals[0])
