@@ -54,3 +54,28 @@ def finalize_feat(partials: torch.Tensor) -> torch.Tensor:
     s, c = partials[:, 0], partials[:, 1]
     per_image = torch.where(c > 0, s / c.clamp_min(1), torch.zeros_like(s)).to(torch.float32)
     return per_image.sum() / partials.shape[0]
+
+
+def allreduce_gradients(params, world_size: int = None, group=None) -> None:
+    """Data-parallel training (outside the north-star forward metric): after ``loss.backward()`` every
+    rank holds the gradient of ITS rays' share of the loss.  With the loss partials all-reduced before the scalars are
+    formed (``hot_path_losses(reduce_fn=...)``) each rank's backward already uses the GLOBAL denominators, so the global
+    gradient is the SUM over ranks -- one all-reduce over a single flat fp32 bucket (2.9 M floats for the 8x512 + 4x512
+    networks: latency-bound over NVLink, no bucketing needed).  Parameters without a gradient contribute zeros so that
+    all ranks build the same bucket."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n

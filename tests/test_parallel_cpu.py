@@ -63,3 +63,54 @@ def test_two_rank_loss_reduction_matches_unsharded():
     ref = O.hot_path_losses(out, scene, 0.5)
     assert abs(ret["rgb"] - float(ref["rgb_loss"])) < 1e-6
     assert abs(ret["feat"] - float(ref["feat_loss"])) < 1e-6
+
+
+def _grad_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mvsdf_b200 import parallel, synth
+    from oracle import mvsdf_oracle as O
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    scene = synth.make_scene(20, 20, n_images=2, n_src=2, seed=6)
+    part = parallel.shard_rays(scene, rank, world)
+    out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), part, None, False)
+    m = out["network_object_mask"] & out["object_mask"]
+    # this rank's share of the rgb loss with the GLOBAL denominator (all rays of all ranks), as after the partial all-reduce
+    n_total = scene["uv"].shape[0] * scene["uv"].shape[1]
+    loss = (out["rgb_values"][m] - part["rgb"].reshape(-1, 3)[m]).abs().sum() / n_total
+    loss.backward()
+    plist = list(params.values())
+    parallel.allreduce_gradients(plist)
+    if rank == 0:
+        ret["grads"] = {k: (p.grad.clone() if p.grad is not None else None) for k, p in params.items()}
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_unsharded_backward():
+    sys.path.insert(0, ROOT)
+    from mvsdf_b200 import synth
+    from oracle import mvsdf_oracle as O
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    scene = synth.make_scene(20, 20, n_images=2, n_src=2, seed=6)
+    out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), scene, None, False)
+    m = out["network_object_mask"] & out["object_mask"]
+    loss = (out["rgb_values"][m] - scene["rgb"].reshape(-1, 3)[m]).abs().sum() / m.numel()
+    loss.backward()
+    checked = 0
+    for k, p in params.items():
+        g = ret["grads"][k]
+        if p.grad is None:
+            assert g is None or float(g.abs().max()) == 0.0
+            continue
+        assert torch.allclose(g, p.grad, rtol=1e-4, atol=1e-7), k
+        checked += 1
+    assert checked >= 20
