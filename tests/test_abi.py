@@ -85,3 +85,36 @@ def test_python_constants_match_the_header():
     c_names = re.findall(r"^\s*(?:float|int)\s+(\w+);", c_fields, re.M)
     assert fields == c_names, (fields, c_names)
     assert ctypes.sizeof(_lib.lib().TracerParams) == 4 * len(c_names)
+
+
+def test_argument_validation_of_the_tracer_and_loss_entry_points(lib):
+    """Every entry point rejects bad arguments with a negative status and a message BEFORE touching the device
+    (so these run without a GPU): null pointers, wrong sample count, short workspaces, wrong channel count."""
+    from mvsdf_b200 import ops
+    P = ctypes.c_void_p
+    net = ops.PackedNet("sdf", 256, 8)
+    prm = lib.TracerParams(1.0, 5e-5, 0.5, 0.5, 3, 10, 100, 8, 0, 2e-3)
+    d = P(256)            # a non-null dummy "device" address; validation must fail before it is dereferenced
+    ws_need = lib.mvsdf_trace_workspace_bytes(1024, 1)
+    args = lambda **kw: [net.handle, kw.get("packed", d), d, d, d, None, ctypes.byref(kw.get("prm", prm)), 1, 1024, 0, d, None,
+                         ctypes.c_size_t(kw.get("ws", ws_need)), d, d, d, d, d, d, d, None]
+    assert lib.mvsdf_trace(*args(packed=None)) == -1 and b"null" in lib.mvsdf_last_error()
+    bad = lib.TracerParams(1.0, 5e-5, 0.5, 0.5, 3, 10, 64, 8, 0, 0.0)
+    assert lib.mvsdf_trace(*args(prm=bad)) == -1 and b"n_steps" in lib.mvsdf_last_error()
+    bad = lib.TracerParams(1.0, 5e-5, 0.5, 0.5, 3, 100, 100, 8, 0, 0.0)
+    assert lib.mvsdf_trace(*args(prm=bad)) == -1 and b"iteration" in lib.mvsdf_last_error()
+    assert lib.mvsdf_trace(*args(ws=ws_need - 4096)) == -3 and b"workspace" in lib.mvsdf_last_error()
+    # training mode needs the caller's CPU-generator samples (ray_tracing.py:287)
+    a = args()
+    a[9] = 1
+    assert lib.mvsdf_trace(*a) == -1 and b"steps01" in lib.mvsdf_last_error()
+    # workspace grows with the ray count and covers the prefilter's lists
+    assert lib.mvsdf_trace_workspace_bytes(1 << 20, 1) > lib.mvsdf_trace_workspace_bytes(1 << 18, 1) > ws_need
+    # feature-consistency forward / backward: 32 channels, >= 2 views, no null pointers
+    assert lib.mvsdf_feat_loss_partials(d, d, d, d, 1, 2, 8, 8, 16, d, d, d, None) == -1 and b"32" in lib.mvsdf_last_error()
+    assert lib.mvsdf_feat_loss_partials(d, d, d, d, 1, 1, 8, 8, 32, d, d, d, None) == -1
+    assert lib.mvsdf_feat_loss_backward(d, d, d, d, 1, 2, 8, 8, 32, d, d, d, None, d, None) == -1
+    assert b"null" in lib.mvsdf_last_error()
+    assert lib.mvsdf_feat_loss_backward(d, d, d, d, 1, 2, 8, 8, 16, d, d, d, d, d, None) == -1
+    assert lib.mvsdf_rgb_l1_partials(d, d, d, 0, d, None) == -1
+    assert lib.mvsdf_depth_loss_partials(d, 2, d, 10, d, d, 1, 8, 8, d, d, 0.5, 1.0, 1.0, 1.0, 1.0, d, d, d, None) == -1
