@@ -7,8 +7,9 @@ IDRNetwork.forward + get_feat_loss_corr + get_rgb_loss.
 
 Workloads (BASELINE.json `configs`):
   cfg2 (default, the configuration the metric is quoted on): DTU-shaped 1200x1600 full image =
-       1.92 M rays, 4 source views, 8x512 SDF MLP + 4x512 rendering MLP, eval mode, one image per GPU
-       (weak scaling: every rank renders its own view of the scene; loss partials are all-reduced).
+       1.92 M rays, 4 source views, 8x512 SDF MLP + 4x512 rendering MLP, eval mode.  With --gpus N the rays of this ONE
+       image are dealt to the ranks in round-robin tiles of --shard-tile rays (strong scaling, SURVEY.md section 8e;
+       loss partials are all-reduced); --scaling weak renders one image per rank instead.
   cfg3: 2 x 4096 rays, 8 source views, train-mode forward (tp = 0.5).
   cfg1: 32x32 rays, 256-wide nets, 1 source view (the CPU-runnable case).
 
@@ -36,7 +37,7 @@ from mvsdf_b200 import synth  # noqa: E402
 METRIC = "rays/sec (sphere-trace+render+feat-loss) at DTU 1200x1600"
 
 WORKLOADS = {
-    "cfg2": dict(H=1200, W=1600, width=512, n_src=4, n_images=1, n_rays=None, training=False,
+    "cfg2": dict(H=1200, W=1600, width=512, n_src=4, n_images=1, n_rays=None, training=False, shard_rays=True,
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
     "cfg3": dict(H=1200, W=1600, width=512, n_src=8, n_images=2, n_rays=4096, training=True,
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
@@ -46,8 +47,8 @@ WORKLOADS = {
     # every rank holds the whole feature maps, the loss partials are all-reduced
     "cfg4": dict(H=1200, W=1600, width=512, n_src=4, n_images=1, n_rays=1200000, training=False, shard_rays=True,
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
-    # configs[4]: Tanks&Temples-shaped 1080p, 12 source views; one image per rank (weak scaling)
-    "cfg5": dict(H=1080, W=1920, width=512, n_src=12, n_images=1, n_rays=None, training=False,
+    # configs[4]: Tanks&Temples-shaped 1080p, 12 source views; the 8-GPU throughput sweep shards ONE image like cfg2
+    "cfg5": dict(H=1080, W=1920, width=512, n_src=12, n_images=1, n_rays=None, training=False, shard_rays=True,
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
 }
 
@@ -108,16 +109,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def make_inputs(cfg, rank, world=1):
-    """Host tensors of one step.  Weak-scaling workloads: every rank renders a different view of the same synthetic
-    scene.  shard_rays workloads: all ranks hold the SAME image and rank r takes the r-th contiguous range of its rays
-    (contiguous ray ranges within an image, maps replicated)."""
-    shard = bool(cfg.get("shard_rays"))
+def make_inputs(cfg, rank, world=1, shard=None, tile=1024):
+    """Host tensors of one step.  Weak scaling: every rank renders a different view of the same synthetic scene.
+    Strong scaling (shard): all ranks hold the SAME image and rank r takes its share of the rays -- round-robin tiles of
+    `tile` consecutive rays (tile 0: one contiguous range) -- with the feature maps replicated."""
+    shard = bool(cfg.get("shard_rays")) if shard is None else shard
     scene = synth.make_scene(cfg["H"], cfg["W"], n_images=cfg["n_images"], n_src=cfg["n_src"], n_rays=cfg["n_rays"],
                              seed=0 if shard else rank)
     if shard and world > 1:
         from mvsdf_b200 import parallel
-        scene = parallel.shard_rays(scene, rank, world)
+        scene = parallel.shard_rays(scene, rank, world, tile=tile)
     sd = synth.make_state_dict(**cfg["weights"])
     return scene, sd
 
@@ -128,6 +129,10 @@ def pin(d):
 
 IN_KEYS = ["uv", "pose", "intrinsics", "object_mask"]
 GT_KEYS = ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center"]
+# constants of the scene (scene_dataset.py:138-149 computes them once per scene): they live in the loss module's
+# channels-last feature store (mvsdf_b200/loss.py FeatureStore) and are NOT part of a step's input
+SCENE_KEYS = ["feat", "feat_src"]
+STEP_KEYS = [k for k in IN_KEYS + GT_KEYS if k not in SCENE_KEYS]
 
 
 def run_ours(args):
@@ -145,9 +150,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = WORKLOADS[args.workload]
-    scene, sd = make_inputs(cfg, rank, world)
+    strong = bool(cfg.get("shard_rays")) and args.scaling == "strong"
+    scene, sd = make_inputs(cfg, rank, world, shard=strong, tile=args.shard_tile)
     B, N = scene["uv"].shape[:2]
     R = B * N
+    r_all = torch.tensor([R], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(r_all)
+    R_total = int(r_all.item())                                  # rays of the whole job (strong: the one image)
     model = B200IDRNetwork(default_conf(cfg["width"])).to(dev)
     model.load_state_dict(sd)
     model.train(cfg["training"])
@@ -195,6 +205,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    ms_local = ms_total / args.steps
     clk = clocks.stop()
     launches = L.mvsdf_launch_count() - launches0
     import ctypes
@@ -207,7 +218,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * R / (ms_per_step * 1e-3)
+    value = R_total / (ms_per_step * 1e-3)
 
     # tracer evaluations of the last step (E_trace of SURVEY 8d: requests the reference algorithm issues)
     cnt = model.last_trace_counters.cpu()
@@ -236,28 +247,43 @@ def run_ours(args):
 
     # ---------------- end-to-end through the public API with host buffers (`e2e`)
     def h2d_step():
-        inputs = {k: host[k].to(dev, non_blocking=True) for k in IN_KEYS + GT_KEYS}
+        inputs = {k: host[k].to(dev, non_blocking=True) for k in STEP_KEYS}
+        for k in SCENE_KEYS:                     # the same host tensors every step: served by the resident feature store
+            inputs[k] = host[k]
         _, ls = step(inputs)
         vals = torch.stack([ls["rgb_loss"].reshape(()), ls["feat_loss"].reshape(())]).cpu()   # D2H of the step's result
         return vals
 
-    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in IN_KEYS + GT_KEYS)
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in STEP_KEYS)
+    scene_bytes = sum(host[k].numel() * host[k].element_size() for k in SCENE_KEYS)
+    restacks0 = None
     d2h_bytes = 8 + 4 * (B + 1)          # the two loss scalars + the hit-count read inside forward()
     for _ in range(max(1, args.warmup // 2)):
         h2d_step()
     barrier()
+    restacks0 = loss_mod.store.restacks
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         vals = h2d_step()
     e1.record()
     barrier()
+    assert loss_mod.store.restacks == restacks0, "the feature store re-uploaded the scene's maps inside the timed region"
     ms_e2e = e0.elapsed_time(e1)
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item()) / args.steps
-    e2e_value = world * R / (ms_e2e * 1e-3)
+    e2e_value = R_total / (ms_e2e * 1e-3)
+    # per-rank load (strong scaling: is the split balanced?)
+    per_rank = torch.tensor([ms_local, float(n_hit), float(R), float(evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
+    else:
+        gathered = [per_rank]
+    per_rank = [dict(rank=i, ms_per_step=float(g[0]), rays=int(g[2]), hit_fraction=float(g[1] / g[2]),
+                     tracer_evals_per_ray=float(g[3] / g[2])) for i, g in enumerate(gathered)]
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -270,15 +296,19 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if cfg.get("shard_rays") else "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None,
             "dtype": "fp32-equivalent (fp16 hi/lo split operands, fp32 tensor-core accumulate)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg['H']}x{cfg['W']} image, {R} rays/GPU, {cfg['n_src']} src views, "
                                    f"8x{width} SDF MLP + 4x{width} render MLP, {'train' if cfg['training'] else 'eval'}-mode forward "
                                    f"+ feat loss + rgb L1", "rays_per_gpu": R, "hit_fraction": n_hit / R,
                        "tracer_evals_per_ray": evals / R,
-                       "parallelism": (f"one image, contiguous ray ranges over {world} ranks" if cfg.get("shard_rays") else
-                                       f"one image per rank, dp{world}") + ", loss-partials all-reduce",
+                       "rays_total": R_total,
+                       "parallelism": ((f"ONE image, rays dealt to {world} ranks in round-robin tiles of {args.shard_tile} rays"
+                                        if args.shard_tile > 0 else f"ONE image, contiguous ray ranges over {world} ranks")
+                                       if strong else f"one image per rank, dp{world}") + ", loss-partials all-reduce",
+                       "per_rank": per_rank,
+                       "feature_store": f"{scene_bytes} bytes of scene feature maps resident channels-last (uploaded once, not per step)",
                        "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
                        "skip_min_sdf": bool(args.skip_min_sdf),
                        "prefilter": {"tau": model.prefilter_tau, "screened_evals_per_ray": screened / R, "refined_evals_per_ray": refined / R,
@@ -445,6 +475,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = shard ONE image's rays over the ranks (default), weak = one image per rank")
+    ap.add_argument("--shard-tile", type=int, default=1024, help="strong scaling: rays per round-robin tile (0 = contiguous ranges)")
     ap.add_argument("--skip-min-sdf", type=int, default=0)
     ap.add_argument("--prefilter-tau", type=float, default=None, help="override B200IDRNetwork.prefilter_tau (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

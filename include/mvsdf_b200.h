@@ -60,6 +60,16 @@ mvsdf_net* mvsdf_render_net_create(int width, int n_hidden, int n_freqs_view, in
 void mvsdf_net_destroy(mvsdf_net* net);
 int mvsdf_net_num_layers(const mvsdf_net* net);          /* number of source Linear layers */
 size_t mvsdf_net_packed_bytes(const mvsdf_net* net);      /* size of the packed blob the caller must allocate */
+/* Numeric-range monitors.  Weights and activations are stored as fp16 hi/lo pairs of 64*x, so |W| or an activation beyond
+ * ~1023 cannot be represented.  int32 words at packed + mvsdf_net_status_offset(net), zeroed by every mvsdf_pack_weights:
+ *   [MVSDF_STATUS_PACK_RANGE]  packed weight elements outside the representable range (or non-finite),
+ *   [MVSDF_STATUS_NONFINITE]   non-finite values written by the heads of the MLP kernels since the last pack (an overflowed
+ *                              activation turns into NaN in the hi/lo split and surfaces there).
+ * A caller reads them at its next host synchronisation and must treat non-zero as an error (B200IDRNetwork raises). */
+#define MVSDF_STATUS_WORDS 4
+#define MVSDF_STATUS_PACK_RANGE 0
+#define MVSDF_STATUS_NONFINITE 1
+size_t mvsdf_net_status_offset(const mvsdf_net* net);
 
 /* Fold weight_norm (W = g * v / ||v||_row, nn.utils.weight_norm dim=0; :70-71, :137-138), scale, split into
  * fp16 hi/lo tiles and write the packed blob.  weight_v_host[l] etc. are HOST arrays of device pointers, one
@@ -170,6 +180,13 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
                              int n_images, int n_views, int h, int w, int channels, const float* size,
                              const float* center, double* partials, void* stream);
 int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_loss, void* stream);
+/* Scene feature store variant: maps_nhwc holds ALL feature maps of a scene once, channels-last [n_maps,h,w,32] (the layout
+ * the reference's dataset would keep instead of self.feats [n_images,32,h,w] on the host, scene_dataset.py:138-149), and
+ * map_index [B,V] (device int32) names the map of every (image, view) -- ground_truth["feat"] = self.feats[idx],
+ * ["feat_src"] = self.feats[src_idxs] (scene_dataset.py:205-207) become index lookups, nothing is copied per step. */
+int mvsdf_feat_loss_partials_indexed(const float* surf_pts, const int32_t* hit_offsets, const float* cams,
+                                     const float* maps_nhwc, const int32_t* map_index, int n_images, int n_views, int h, int w,
+                                     int channels, const float* size, const float* center, double* partials, void* stream);
 /* Backward of the same term w.r.t. the surface points (what autograd computes through F.grid_sample, the projections and
  * the cosine similarity, loss.py:132-155; the feature maps are constants):  out_grad_pts [M,3] = upstream_grad[0] *
  * d loss / d surf_pts, with partials [B,2] as left by mvsdf_feat_loss_partials (after the all-reduce in a multi-GPU run:
@@ -177,6 +194,10 @@ int mvsdf_feat_loss_finalize(const double* partials, int n_images, float* out_lo
 int mvsdf_feat_loss_backward(const float* surf_pts, const int32_t* hit_offsets, const float* cams, const float* maps_nhwc,
                              int n_images, int n_views, int h, int w, int channels, const float* size, const float* center,
                              const double* partials, const float* upstream_grad, float* out_grad_pts, void* stream);
+int mvsdf_feat_loss_backward_indexed(const float* surf_pts, const int32_t* hit_offsets, const float* cams,
+                                     const float* maps_nhwc, const int32_t* map_index, int n_images, int n_views, int h, int w,
+                                     int channels, const float* size, const float* center, const double* partials,
+                                     const float* upstream_grad, float* out_grad_pts, void* stream);
 
 /* ---- IDRLoss.get_depth_loss (code/model/loss.py:37-63) with carving_t2 + RunningTopK (code/utils/my_utils.py:168-201,
  * :269-331), use_invalid=False, smooth=None: for every eikonal point, the signed gap to the MVS depth surface along the

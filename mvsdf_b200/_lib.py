@@ -42,6 +42,8 @@ def _declare(lib):
     lib.mvsdf_net_num_layers.argtypes = [P]
     lib.mvsdf_net_packed_bytes.restype = c_size_t
     lib.mvsdf_net_packed_bytes.argtypes = [P]
+    lib.mvsdf_net_status_offset.restype = c_size_t
+    lib.mvsdf_net_status_offset.argtypes = [P]
     lib.mvsdf_pack_weights.restype = c_int
     lib.mvsdf_pack_weights.argtypes = [P, POINTER(P), POINTER(P), POINTER(P), P, P]
     lib.mvsdf_sdf_forward.restype = c_int
@@ -73,6 +75,10 @@ def _declare(lib):
     lib.mvsdf_feat_loss_partials.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
     lib.mvsdf_feat_loss_backward.restype = c_int
     lib.mvsdf_feat_loss_backward.argtypes = [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]
+    lib.mvsdf_feat_loss_partials_indexed.restype = c_int
+    lib.mvsdf_feat_loss_partials_indexed.argtypes = [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]
+    lib.mvsdf_feat_loss_backward_indexed.restype = c_int
+    lib.mvsdf_feat_loss_backward_indexed.argtypes = [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]
     lib.mvsdf_feat_loss_finalize.restype = c_int
     lib.mvsdf_feat_loss_finalize.argtypes = [P, c_int, P, P]
     lib.mvsdf_depth_loss_partials.restype = c_int

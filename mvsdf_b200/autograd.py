@@ -193,15 +193,16 @@ def _feat_loss_torch(pts, hit_offsets: List[int], counts, feat, cam, feat_src, s
 
 
 class FeatConsistency(torch.autograd.Function):
-    """loss = FeatConsistency.apply(loss_module, pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn).
+    """loss = FeatConsistency.apply(loss_module, pts, hit_offsets, maps, map_index, cam, src_cams, size, center, reduce_fn).
     Forward = mvsdf_feat_loss_partials / _finalize; backward = mvsdf_feat_loss_backward (native: projections, bilinear
     tap derivatives and the cosine-similarity chain in one kernel).  ``_feat_loss_torch`` above is kept as the
     differentiable statement the native backward is tested against (tests/test_gpu_autograd.py)."""
 
     @staticmethod
-    def forward(ctx, module, pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn):
-        out = module._feat_loss_native(pts, hit_offsets, feat, cam, feat_src, src_cams, size, center, reduce_fn)
+    def forward(ctx, module, pts, hit_offsets, maps, map_index, cam, src_cams, size, center, reduce_fn):
+        out = module._feat_loss_native(pts, hit_offsets, maps, map_index, cam, src_cams, size, center, reduce_fn)
         ctx.module = module
+        ctx.map_index = map_index
         ctx.n_pts = pts.shape[0]
         ctx.pts_shape = pts.shape
         ctx.save_for_backward(module.last_partials["feat"], *module._feat_ctx)
@@ -212,5 +213,5 @@ class FeatConsistency(torch.autograd.Function):
         partial, *operands = ctx.saved_tensors
         if ctx.n_pts == 0:
             return None, g.new_zeros(ctx.pts_shape), None, None, None, None, None, None, None, None
-        gp = ctx.module._feat_loss_backward_native(operands, partial, g)
+        gp = ctx.module._feat_loss_backward_native(operands, partial, g, ctx.map_index)
         return None, gp, None, None, None, None, None, None, None, None

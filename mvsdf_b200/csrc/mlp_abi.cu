@@ -12,7 +12,6 @@
 
 #include "../../include/mvsdf_b200.h"
 #include "internal.h"
-#include "mlp_pair_kernel.cuh"
 #include "mlp_pair2_kernel.cuh"
 
 struct mvsdf_net {
@@ -98,6 +97,9 @@ static void finalize_plan(NetPlan& p) {
     sc += rows;
   }
   off += (long long)sc * 4;
+  off = (off + 255) / 256 * 256;
+  p.status_off = off;
+  off += kStatusWords * 4;
   p.total_bytes = (off + 255) / 256 * 256;
 }
 
@@ -119,7 +121,7 @@ __global__ void row_scale_kernel(const float* __restrict__ v, const float* __res
 // one thread per (padded destination row, 8-wide K core): 16 B of hi and 16 B of lo
 __global__ void pack_layer_kernel(const float* __restrict__ v, const float* __restrict__ scale,
                                   const float* __restrict__ bias_src, LayerPlan lp, int feat_size,
-                                  uint8_t* __restrict__ packed, float* __restrict__ bias_dst) {
+                                  uint8_t* __restrict__ packed, float* __restrict__ bias_dst, int* __restrict__ status) {
   const int cores = lp.k_chunks * (kChunkK / 8);
   const int rows = lp.m_tiles * kTileM;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,6 +139,7 @@ __global__ void pack_layer_kernel(const float* __restrict__ v, const float* __re
     const int k = kcore * 8 + e;
     float w = 0.f;
     if (sr >= 0 && k < lp.in_dim) w = v[(size_t)sr * lp.in_dim + k] * sc * lp.col_scale * kWeightScale;
+    if (!(fabsf(w) < 65504.0f)) atomicAdd(status + kStatusPackRange, 1);      // beyond fp16 (or NaN): the hi part would be inf
     hi[e] = __float2half_rn(w);
     lo[e] = __float2half_rn(w - __half2float(hi[e]));
   }
@@ -156,6 +159,7 @@ static int fill_args(const NetPlan& p, const void* packed, int head, MlpArgs& a)
   a.trace = g_trace;
   a.packed = static_cast<const uint8_t*>(packed);
   a.bias = reinterpret_cast<const float*>(a.packed + p.bias_area_off);
+  a.status = reinterpret_cast<int*>(const_cast<uint8_t*>(a.packed) + p.status_off);
   a.n_run = p.n_hidden + 1;
   a.skip_layer = p.skip_layer;
   a.skip_rows_begin = p.skip_rows_begin;
@@ -224,8 +228,7 @@ static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, b
   const size_t smem = mlp_smem_bytes(p.k_cores_max);
   // the screening-precision instantiation exists for the plain SDF evaluation only (the tracer's sampler prefilter)
   constexpr bool kCanLp = KIND == NET_SDF && MODE == 0 && VER == 2;
-  auto kern = VER == 2 ? ((kCanLp && a.lp) ? mlp_pair2_kernel<KIND, MODE, kCanLp ? 1 : 0> : mlp_pair2_kernel<KIND, MODE, 0>)
-                       : mlp_pair_kernel<KIND, MODE>;
+  auto kern = (kCanLp && a.lp) ? mlp_pair2_kernel<KIND, MODE, kCanLp ? 1 : 0> : mlp_pair2_kernel<KIND, MODE, 0>;
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(mlp_pair_kernel)");
   if (rc) return rc;
@@ -234,7 +237,7 @@ static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, b
   const int kind = KIND == NET_RENDER ? 3 : (MODE == 1 ? 2 : (a.head == HEAD_FULL ? 1 : ((kCanLp && a.lp) ? 4 : 0)));
   ProfEvent* pe = prof_begin(kind, st);
   note_launch();
-  kern<<<2 * n_pairs, VER == 2 ? kP2Threads : kMlpThreads, smem, st>>>(a);
+  kern<<<2 * n_pairs, kP2Threads, smem, st>>>(a);
   prof_end(pe, st);
   return check_cuda(cudaGetLastError(), "launch mlp_pair_kernel");
 }
@@ -252,10 +255,9 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
   // small host-known batches cannot fill clusters: fall back to single-CTA scheduling (same kernel, CL = 1)
   const bool small = n_dev == nullptr && tiles < 2 * sm_count();
-  // 2 = split-K pipelined pair kernel (default), 1 = layer-synchronous pair kernel, 0 = single-CTA kernel
-  static const int pair = env_int("MVSDF_PAIR", 2);
-  if (pair >= 2 && !small) return launch_mlp_pair<KIND, MODE, 2>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
-  if (pair && !small) return launch_mlp_pair<KIND, MODE, 1>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
+  // 1 = split-K pipelined CTA-pair kernel (default), 0 = single-CTA kernel (A/B runs)
+  static const int pair = env_int("MVSDF_PAIR", 1);
+  if (pair && !small) return launch_mlp_pair<KIND, MODE, 2>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);
   if (cl >= 4 && !small) return launch_mlp_cl<KIND, MODE, 4>(p, a, tiles, n_dev != nullptr, st);
   if (cl >= 2 && !small) return launch_mlp_cl<KIND, MODE, 2>(p, a, tiles, n_dev != nullptr, st);
   return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, n_dev != nullptr, st);
@@ -423,6 +425,7 @@ mvsdf_net* mvsdf_render_net_create(int width, int n_hidden, int n_freqs_view, in
 void mvsdf_net_destroy(mvsdf_net* net) { delete net; }
 int mvsdf_net_num_layers(const mvsdf_net* net) { return net ? net->plan.n_src_layers : 0; }
 size_t mvsdf_net_packed_bytes(const mvsdf_net* net) { return net ? (size_t)net->plan.total_bytes : 0; }
+size_t mvsdf_net_status_offset(const mvsdf_net* net) { return net ? (size_t)net->plan.status_off : 0; }
 
 int mvsdf_pack_weights(const mvsdf_net* net, const float* const* weight_v_host, const float* const* weight_g_host,
                        const float* const* bias_host, void* packed, void* stream) {
@@ -433,6 +436,9 @@ int mvsdf_pack_weights(const mvsdf_net* net, const float* const* weight_v_host, 
   uint8_t* blob = static_cast<uint8_t*>(packed);
   float* scale = reinterpret_cast<float*>(blob + p.scale_area_off);
   float* bias_dst = reinterpret_cast<float*>(blob + p.bias_area_off);
+  int* status = reinterpret_cast<int*>(blob + p.status_off);
+  int rc0 = check_cuda(cudaMemsetAsync(status, 0, kStatusWords * 4, st), "memset status");
+  if (rc0) return rc0;
   for (int s = 0; s < p.n_src_layers; ++s) {
     int rows = 0, cols = 0;
     for (int i = 0; i < p.n_layers; ++i)
@@ -448,7 +454,7 @@ int mvsdf_pack_weights(const mvsdf_net* net, const float* const* weight_v_host, 
     const LayerPlan& L = p.L[i];
     const int total = L.m_tiles * kTileM * L.k_chunks * (kChunkK / 8);
     note_launch(); pack_layer_kernel<<<ceil_div(total, 256), 256, 0, st>>>(weight_v_host[L.src_layer], scale + p.scale_off[L.src_layer],
-                                                            bias_host[L.src_layer], L, p.feat_size, blob, bias_dst);
+                                                            bias_host[L.src_layer], L, p.feat_size, blob, bias_dst, status);
   }
   return check_cuda(cudaGetLastError(), "pack_weights launch");
 }

@@ -62,12 +62,21 @@ struct MlpArgs {
   float* out_full;           // [n, 2+feat]    (HEAD_FULL)
   float* out_grad;           // [n,3]          (value+gradient mode)
   float* out_rgb;            // [n,3]          (render)
+  int* status;               // packed blob's status words (netplan.h kStatus*)
   unsigned long long* trace; // debug only: clock64 timeline of pair 0 (tools/diag_trace.py); nullptr in production
   LayerPlan L[10];
 };
 
 __host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
   return (size_t)kStages * kStageBytes + (size_t)k_cores_max * kBCoreStride + kPeTileBytes + 256;
+}
+
+// Range monitor: activations are stored as fp16 hi/lo of kActScale * x, so |x| >= 1023 overflows to inf; the split then
+// yields NaN (inf - inf), which poisons every accumulator of that column and surfaces at the head.  Checking the values
+// the head writes therefore catches any overflow on the way at the cost of one predicate per OUTPUT element.
+__device__ __forceinline__ float checked(float v, int* status) {
+  if (!(fabsf(v) <= 3.0e38f) && status) atomicAdd(status + kStatusNonFinite, 1);
+  return v;
 }
 
 // byte offset of (column n, feature k) inside an activation operand buffer
@@ -452,26 +461,26 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
                 const float acc = __uint_as_float(v[j]) * kInvScale;
                 if (KIND == NET_RENDER) {
                   const long long gp = p0 + col;
-                  if (row < 3 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
+                  if (row < 3 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(checked(acc + bias, a.status));
                 } else {
                   const long long gp = (MODE == 0) ? p0 + col : p0 + (col >> 2);
                   const int jj = (MODE == 0) ? 0 : (col & 3);
                   if (gp < n_pts) {
                     if (a.head == HEAD_SDF_ONLY) {
                       if (row == 0) {
-                        if (jj == 0) a.out_sdf[gp] = acc + bias;
-                        else a.out_grad[gp * 3 + jj - 1] = acc;
+                        if (jj == 0) a.out_sdf[gp] = checked(acc + bias, a.status);
+                        else a.out_grad[gp * 3 + jj - 1] = checked(acc, a.status);
                       }
                     } else {
                       const int F = a.feat_size;
                       if (jj == 0) {
                         if (f < F) a.out_full[gp * (F + 2) + 2 + f] = acc + bias;
                         else if (f < F + 2) {
-                          a.out_full[gp * (F + 2) + (f - F)] = acc + bias;
+                          a.out_full[gp * (F + 2) + (f - F)] = checked(acc + bias, a.status);
                           if (f == F && a.out_sdf) a.out_sdf[gp] = acc + bias;
                         }
                       } else if (f == F) {
-                        a.out_grad[gp * 3 + jj - 1] = acc;
+                        a.out_grad[gp * 3 + jj - 1] = checked(acc, a.status);
                       }
                     }
                   }

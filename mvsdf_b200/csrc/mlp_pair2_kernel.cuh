@@ -529,34 +529,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                   if (LP) {       // SDF-only head, two column blocks
                     const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;
                     if (f == 0) {
-                      if (gp < n_pts) a.out_sdf[gp] = __uint_as_float(va[hcol][j]) * kInvScale + bias;
-                      if (gp + kTileN < n_pts) a.out_sdf[gp + kTileN] = __uint_as_float(vb[hcol][j]) * kInvScale + bias;
+                      if (gp < n_pts) a.out_sdf[gp] = checked(__uint_as_float(va[hcol][j]) * kInvScale + bias, a.status);
+                      if (gp + kTileN < n_pts) a.out_sdf[gp + kTileN] = checked(__uint_as_float(vb[hcol][j]) * kInvScale + bias, a.status);
                     }
                     continue;
                   }
                   const float acc = (__uint_as_float(va[hcol][j]) + __uint_as_float(vb[hcol][j])) * kInvScale;
                   if (KIND == NET_RENDER) {
                     const long long gp = p0_pair + (long long)ccta * kPtsPerCta + lc;
-                    if (row < 3 && m == 0 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(acc + bias);
+                    if (row < 3 && m == 0 && gp < n_pts) a.out_rgb[gp * 3 + row] = tanhf(checked(acc + bias, a.status));
                   } else {
                     const long long gp = p0_pair + (long long)ccta * kPtsPerCta + ((MODE == 0) ? lc : (lc >> 2));
                     const int jj = (MODE == 0) ? 0 : (lc & 3);
                     if (gp < n_pts) {
                       if (a.head == HEAD_SDF_ONLY) {
                         if (f == 0) {
-                          if (jj == 0) a.out_sdf[gp] = acc + bias;
-                          else a.out_grad[gp * 3 + jj - 1] = acc;
+                          if (jj == 0) a.out_sdf[gp] = checked(acc + bias, a.status);
+                          else a.out_grad[gp * 3 + jj - 1] = checked(acc, a.status);
                         }
                       } else {
                         const int F = a.feat_size;
                         if (jj == 0) {
                           if (f < F) a.out_full[gp * (F + 2) + 2 + f] = acc + bias;
                           else if (f < F + 2) {
-                            a.out_full[gp * (F + 2) + (f - F)] = acc + bias;
+                            a.out_full[gp * (F + 2) + (f - F)] = checked(acc + bias, a.status);
                             if (f == F && a.out_sdf) a.out_sdf[gp] = acc + bias;
                           }
                         } else if (f == F) {
-                          a.out_grad[gp * 3 + jj - 1] = acc;
+                          a.out_grad[gp * 3 + jj - 1] = checked(acc, a.status);
                         }
                       }
                     }

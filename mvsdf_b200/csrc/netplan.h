@@ -34,6 +34,11 @@ constexpr float kActScale = 64.0f;
 constexpr int kMaxLayers = 12;
 constexpr int kTmemCols = 512;                     // 4 output tiles x (64 + 64) accumulator columns
 
+// status words at the end of the packed blob (zeroed by every mvsdf_pack_weights)
+constexpr int kStatusWords = 4;
+constexpr int kStatusPackRange = 0;   // packed weight elements with |kWeightScale * W| beyond the fp16 range (or non-finite)
+constexpr int kStatusNonFinite = 1;   // non-finite head outputs written by the MLP kernels (an activation left the fp16 range)
+
 enum Act : int { ACT_NONE = 0, ACT_SOFTPLUS100 = 1, ACT_RELU = 2 };
 enum NetKind : int { NET_SDF = 0, NET_RENDER = 1 };
 enum HeadKind : int { HEAD_SDF_ONLY = 0, HEAD_FULL = 1 };
@@ -65,6 +70,7 @@ struct NetPlan {
   int feat_size;
   long long bias_area_off;
   long long scale_area_off;   // fp32 g/||v|| per source row, scratch of the packer
+  long long status_off;       // int32[kStatusWords]: range / non-finite monitors (see kStatus*)
   int n_src_layers;
   int scale_off[kMaxLayers];  // float index per source layer
   long long total_bytes;

@@ -170,6 +170,7 @@ struct FeatArgs {
   const float* center;     // [3]
   double* partial;         // [B,2] (sum, count)
   int B, V, h, w;
+  const int* map_index;    // optional [B,V]: map (b, v) is maps[map_index[b*V+v]] (scene feature store); nullptr: b*V+v
 };
 
 __device__ __forceinline__ float dot4(const float* m, float x, float y, float z, float w) {
@@ -248,7 +249,8 @@ __global__ void feat_loss_kernel(FeatArgs a) {
       gx = fminf(fmaxf(gx, -1.1f), 1.1f);
       gy = fminf(fmaxf(gy, -1.1f), 1.1f);
       const bool in = gx <= 1.f && gx >= -1.f && gy <= 1.f && gy >= -1.f;
-      const float* map = a.maps + ((size_t)img * a.V + v) * (size_t)a.h * a.w * 32;
+      const size_t mi = a.map_index ? (size_t)a.map_index[img * a.V + v] : (size_t)img * a.V + v;
+      const float* map = a.maps + mi * (size_t)a.h * a.w * 32;
       const float f = sample_bilinear(map, a.h, a.w, gx, gy, lane);
       const float nrm = sqrtf(warp_sum(f * f));
       if (v == 0) {
@@ -354,6 +356,7 @@ struct FeatBwdArgs {
   const float* upstream;   // [1] d L / d loss
   float* grad;             // [M,3]
   int B, V, h, w;
+  const int* map_index;    // see FeatArgs
 };
 
 __global__ void feat_loss_bwd_kernel(FeatBwdArgs a) {
@@ -373,13 +376,15 @@ __global__ void feat_loss_bwd_kernel(FeatBwdArgs a) {
     const float Y = __fadd_rn(__fmul_rn(__fmul_rn(a.pts[3 * (size_t)p + 1], 0.5f), size), cy);
     const float Z = __fadd_rn(__fmul_rn(__fmul_rn(a.pts[3 * (size_t)p + 2], 0.5f), size), cz);
     const size_t map_stride = (size_t)a.h * a.w * 32;
-    const ViewSample s0 = project_and_sample(a.cams + ((size_t)img * a.V) * 32, a.maps + ((size_t)img * a.V) * map_stride, a.h, a.w,
+    const size_t mi0 = a.map_index ? (size_t)a.map_index[img * a.V] : (size_t)img * a.V;
+    const ViewSample s0 = project_and_sample(a.cams + ((size_t)img * a.V) * 32, a.maps + mi0 * map_stride, a.h, a.w,
                                              X, Y, Z, 0.5f * size, lane);
     const float n0 = sqrtf(warp_sum(s0.f * s0.f));
     const float N0 = fmaxf(n0, 1e-9f);
     float g[3] = {0.f, 0.f, 0.f};
     for (int v = 1; v < a.V; ++v) {
-      const ViewSample sv = project_and_sample(a.cams + ((size_t)img * a.V + v) * 32, a.maps + ((size_t)img * a.V + v) * map_stride,
+      const size_t miv = a.map_index ? (size_t)a.map_index[img * a.V + v] : (size_t)img * a.V + v;
+      const ViewSample sv = project_and_sample(a.cams + ((size_t)img * a.V + v) * 32, a.maps + miv * map_stride,
                                                a.h, a.w, X, Y, Z, 0.5f * size, lane);
       const float nv = sqrtf(warp_sum(sv.f * sv.f));
       const float Nv = fmaxf(nv, 1e-9f);
@@ -699,6 +704,13 @@ int mvsdf_feat_nchw_to_nhwc(const float* src, int n, int channels, int h, int w,
 int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, const float* cams, const float* maps_nhwc,
                              int n_images, int n_views, int h, int w, int channels, const float* size,
                              const float* center, double* partials, void* stream) {
+  return mvsdf_feat_loss_partials_indexed(surf_pts, hit_offsets, cams, maps_nhwc, nullptr, n_images, n_views, h, w, channels, size,
+                                          center, partials, stream);
+}
+
+int mvsdf_feat_loss_partials_indexed(const float* surf_pts, const int32_t* hit_offsets, const float* cams,
+                                     const float* maps_nhwc, const int32_t* map_index, int n_images, int n_views, int h, int w,
+                                     int channels, const float* size, const float* center, double* partials, void* stream) {
   if (!surf_pts || !hit_offsets || !cams || !maps_nhwc || !size || !center || !partials)
     return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_partials: null argument");
   if (channels != 32) return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_partials: 32 feature channels expected (FeatExt, my_utils.py:697-708)");
@@ -706,7 +718,7 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = check_cuda(cudaMemsetAsync(partials, 0, sizeof(double) * 2 * n_images, st), "memset partials");
   if (rc) return rc;
-  FeatArgs a{surf_pts, hit_offsets, cams, maps_nhwc, size, center, partials, n_images, n_views, h, w};
+  FeatArgs a{surf_pts, hit_offsets, cams, maps_nhwc, size, center, partials, n_images, n_views, h, w, map_index};
   const int sms = sm_count();
   if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
   note_launch(); feat_counts_kernel<<<(n_images + 63) / 64, 64, 0, st>>>(hit_offsets, n_images, n_views, partials);
@@ -717,6 +729,14 @@ int mvsdf_feat_loss_partials(const float* surf_pts, const int32_t* hit_offsets, 
 int mvsdf_feat_loss_backward(const float* surf_pts, const int32_t* hit_offsets, const float* cams, const float* maps_nhwc,
                              int n_images, int n_views, int h, int w, int channels, const float* size, const float* center,
                              const double* partials, const float* upstream_grad, float* out_grad_pts, void* stream) {
+  return mvsdf_feat_loss_backward_indexed(surf_pts, hit_offsets, cams, maps_nhwc, nullptr, n_images, n_views, h, w, channels, size,
+                                          center, partials, upstream_grad, out_grad_pts, stream);
+}
+
+int mvsdf_feat_loss_backward_indexed(const float* surf_pts, const int32_t* hit_offsets, const float* cams,
+                                     const float* maps_nhwc, const int32_t* map_index, int n_images, int n_views, int h, int w,
+                                     int channels, const float* size, const float* center, const double* partials,
+                                     const float* upstream_grad, float* out_grad_pts, void* stream) {
   if (!surf_pts || !hit_offsets || !cams || !maps_nhwc || !size || !center || !partials || !upstream_grad || !out_grad_pts)
     return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_backward: null argument");
   if (channels != 32) return fail(MVSDF_ERR_INVALID, "mvsdf_feat_loss_backward: 32 feature channels expected");
@@ -724,7 +744,7 @@ int mvsdf_feat_loss_backward(const float* surf_pts, const int32_t* hit_offsets, 
   const int sms = sm_count();
   if (sms <= 0) return fail(MVSDF_ERR_CUDA, "no CUDA device (the product path has no CPU fallback)");
   FeatBwdArgs a{surf_pts, hit_offsets, cams, maps_nhwc, size, center, partials, upstream_grad, out_grad_pts,
-                n_images, n_views, h, w};
+                n_images, n_views, h, w, map_index};
   note_launch(); feat_loss_bwd_kernel<<<sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return check_cuda(cudaGetLastError(), "feat_loss_bwd launch");
 }

@@ -319,9 +319,26 @@ __global__ void sampler_select_kernel(TraceCtx c, const float* __restrict__ lin,
 //     screening minimum.
 // After the merge the selection kernels run unchanged; un-refined samples keep their screening values, of which only
 // the (certain) sign and the (certain) fact that they are not the minimum is used.
-__device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int li, const unsigned char* want) {
+// Unbiased guard: the refined samples are the near-surface / near-minimum ones, where the screening error is smallest, so
+// checking only them would under-report it.  A pseudo-random 1/kAuditPeriod of the screened samples that are NOT refined
+// (their screening value is trusted for its sign / non-minimality) is therefore evaluated exactly as well -- only to be
+// compared: want[i] == 2 marks such an audit sample, its ref_src is stored negated and the merge kernel leaves req_val alone.
+constexpr unsigned kAuditPeriod = 64;
+__device__ __forceinline__ bool audit_pick(unsigned sample_index, unsigned salt) {
+  unsigned h = (sample_index + salt * 0x9E3779B9u) * 2654435761u;
+  h ^= h >> 15;
+  h *= 2246822519u;
+  h ^= h >> 13;
+  return (h % kAuditPeriod) == 0u;
+}
+
+__device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int li, unsigned char* want) {
+  const float* f = c.req_val + (size_t)li * kSteps;
   int n = 0;
-  for (int i = 0; i < kSteps; ++i) n += want[i];
+  for (int i = 0; i < kSteps; ++i) {
+    if (!want[i] && f[i] != INFINITY && audit_pick((unsigned)(li * kSteps + i), (unsigned)counter)) want[i] = 2;
+    n += want[i] ? 1 : 0;
+  }
   if (n == 0) return;
   int slot = atomicAdd(c.ref_counters + counter, n);
   for (int i = 0; i < kSteps; ++i)
@@ -330,7 +347,7 @@ __device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int 
       c.ref_pts[3 * (size_t)slot] = c.req_pts[3 * src];
       c.ref_pts[3 * (size_t)slot + 1] = c.req_pts[3 * src + 1];
       c.ref_pts[3 * (size_t)slot + 2] = c.req_pts[3 * src + 2];
-      c.ref_src[slot] = (int)src;
+      c.ref_src[slot] = want[i] == 2 ? -1 - (int)src : (int)src;
       ++slot;
     }
 }
@@ -439,15 +456,20 @@ __global__ void prefilter_argmin_kernel(TraceCtx c, float tau, int list_counter,
   push_refine(c, counter, li, want);
 }
 
-// exact values replace the screening values; kCtrViolations counts samples whose screening error exceeded tau / 2
+// exact values replace the screening values; kCtrViolations counts samples (refined ones and the audited un-refined ones,
+// see audit_pick) whose screening error exceeded tau / 2
 __global__ void prefilter_merge_kernel(TraceCtx c, float tau, int counter) {
   const int n = c.ref_counters[counter];
   if (blockIdx.x == 0 && threadIdx.x == 0) c.counters[kCtrRefined] += n;      // launches of one stream: no race
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int src = c.ref_src[i];
+    const int raw = c.ref_src[i];
+    const int src = raw < 0 ? -1 - raw : raw;
     const float exact = c.ref_val[i], lp = c.req_val[src];
-    if (lp != INFINITY && !(fabsf(exact - lp) <= 0.5f * tau)) atomicAdd(c.counters + kCtrViolations, 1);   // +inf: never screened
-    c.req_val[src] = exact;
+    // soundness needs |error| < tau everywhere; the guard trips at tau/2 on refined samples (near the surface, where the
+    // error is smallest) and at 3/4 tau on audited ones (anywhere along the ray)
+    const float lim = raw < 0 ? 0.75f * tau : 0.5f * tau;
+    if (lp != INFINITY && !(fabsf(exact - lp) <= lim)) atomicAdd(c.counters + kCtrViolations, 1);   // +inf: never screened
+    if (raw >= 0) c.req_val[src] = exact;      // audit samples are only compared: the outputs do not depend on the audit
   }
 }
 
@@ -612,6 +634,18 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     return fail(MVSDF_ERR_INVALID, "mvsdf_trace: steps01 is required in training mode (CPU-generator samples, ray_tracing.py:287)");
   const int64_t R = (int64_t)n_images * n_pixels;
   if (R <= 0 || R > (1ll << 30)) return fail(MVSDF_ERR_INVALID, "mvsdf_trace: bad ray count");
+  {
+    // every request phase owns one device counter below kCtrScreened: refuse configurations that would run into the
+    // fixed slots (and from there into the prefilter's counters) BEFORE anything is launched
+    const int64_t batches = (R + (1 << 18) - 1) / (1 << 18);
+    const int64_t need = 1 + (int64_t)prm->sphere_tracing_iters * (1 + prm->line_step_iters) + batches + prm->n_secant_steps +
+                         ((training && !prm->skip_min_sdf) ? batches : 0);
+    if (need >= kCtrScreened)
+      return fail(MVSDF_ERR_INVALID,
+                  "mvsdf_trace: %lld request phases (1 + sphere_tracing_iters*(1+line_step_iters) + sampler/min-sdf batches + "
+                  "secant steps) exceed the %d request counters",
+                  (long long)need, kCtrScreened);
+  }
   if (workspace_bytes < mvsdf_trace_workspace_bytes(R, n_images))
     return fail(MVSDF_ERR_WORKSPACE, "mvsdf_trace: workspace too small (%zu < %zu)", workspace_bytes,
                 mvsdf_trace_workspace_bytes(R, n_images));

@@ -180,8 +180,10 @@ class ImplicitNetwork(_PackedMlp):
     def sdf_grid(self, resolution: int, bound: float = 1.0, chunk: int = 1 << 24) -> torch.Tensor:
         """SDF on a dense resolution^3 grid over [-bound, bound]^3 -- the evaluation utils/plots.py:113-163 (get_surface_trace /
         get_grid_uniform) feeds to marching cubes, 50 000 points per MLP call there.  One launch of
-        the fused SDF-only-head kernel per `chunk` points; returns [resolution, resolution, resolution] indexed [x, y, z]
-        like np.meshgrid(x, y, z) flattened the way plots.py:182-190 does (xx, yy, zz = meshgrid; points = stack(ravel))."""
+        the fused SDF-only-head kernel per `chunk` points.  Returns [resolution, resolution, resolution] indexed **[y, x, z]**:
+        the flat order is exactly that of plots.py's get_grid_uniform (np.meshgrid(x, y, z) with the default 'xy' indexing,
+        then ravel), so -- like plots.py:126-128 -- a caller transposes with .permute(1, 0, 2) before marching cubes to get
+        [x, y, z]."""
         dev = self.lin0.weight_v.device
         ax = torch.linspace(-bound, bound, resolution, device=dev)
         net = self.packed()
@@ -274,7 +276,9 @@ class B200IDRNetwork(nn.Module):
         self.skip_min_sdf = False          # minimal_sdf_points feeds no MVSDF loss; keep for parity
         # > 0: the tracer's 100-sample stages screen all samples with the single-product kernel and evaluate exactly
         # only the samples the selection logic can depend on (include/mvsdf_b200.h, prefilter_tau); results are
-        # bit-identical to 0.0 (off) unless counters[255] (screening error > tau/2 seen) is non-zero
+        # bit-identical to 0.0 (off) as long as the screening error stays below tau.  counters[255] (the guard) counts
+        # samples whose measured |screening - exact| exceeded tau/2: all refined samples plus a pseudo-random 1/64 of the
+        # un-refined ones (re-evaluated exactly for this purpose only) -- a statistical monitor, not a proof
         self.prefilter_tau = float(os.environ.get("MVSDF_PREFILTER_TAU", DEFAULT_PREFILTER_TAU))
         self.prefilter_fallbacks = 0       # forwards repeated exactly because the screening guard tripped
         self._ws: Dict[str, torch.Tensor] = {}
@@ -381,18 +385,37 @@ class B200IDRNetwork(nn.Module):
         (mvsdf_b200/autograd.py) so that the reference's ``loss.backward()`` reaches the parameters."""
         wants_grad = (self.training and torch.is_grad_enabled()
                       and any(p.requires_grad for p in self.parameters()))
+        if self.training:
+            # draw the step's CPU-generator randomness ONCE, in the reference's order (tracer steps :287 first, then the
+            # eikonal samples :216-221), so that a prefilter fallback (_redo_exact) replays the same draws instead of
+            # consuming the RNG streams twice
+            if steps01 is None and not self.skip_min_sdf:
+                steps01 = torch.empty(self.tracer_conf["n_steps"]).uniform_(0.0, 1.0)
+            if eik_points is None:
+                r = self.object_bounding_sphere
+                B_, N_ = input["uv"].shape[:2]
+                eik_points = torch.empty(B_ * N_ // 2, 3).uniform_(-r, r)
         if wants_grad:
             return self._forward_autograd(input, train_progress, steps01, eik_points, dsurf_rand)
         with torch.no_grad():
             return self._forward_native(input, train_progress, steps01, eik_points, dsurf_rand)
 
-    def _screening_failed(self) -> bool:
-        """True when the tracer's prefilter saw a screening error above tau/2 (counter 255): its bit-exactness argument
-        needs error < tau, so the caller repeats the forward with the prefilter off.  Called right after a host
-        sync the forward needs anyway."""
-        if self.prefilter_tau <= 0.0 or self.last_trace_counters is None:
-            return False
-        return int(self.last_trace_counters[_lib.CTR_VIOLATIONS].item()) != 0
+    def _host_checks(self, sdf_net, rend_net, count: torch.Tensor):
+        """The forward's single device->host read: the data-dependent number of surface points, the prefilter guard
+        (counter 255: a screening error above the guard threshold was seen -- its bit-exactness argument needs error < tau,
+        so the caller repeats the forward with the prefilter off) and the fp16-range monitors of both packed nets
+        (raises: the fp16 hi/lo representation was exceeded, results would be garbage).  Returns (count, screening_failed)."""
+        parts = [count.reshape(1).to(torch.int32), self.last_trace_counters[_lib.CTR_VIOLATIONS:_lib.CTR_VIOLATIONS + 1],
+                 sdf_net.status()[:2], rend_net.status()[:2]]
+        h = torch.cat(parts).cpu()
+        for net, off in ((sdf_net, 2), (rend_net, 4)):
+            if int(h[off]) != 0:
+                raise _lib.MvsdfError(f"{net.kind} net: {int(h[off])} packed weight elements have |64*W| beyond the fp16 range "
+                                      "(|W| >= 1023.5 or non-finite); the fp16 hi/lo split cannot represent this network")
+            if int(h[off + 1]) != 0:
+                raise _lib.MvsdfError(f"{net.kind} net: {int(h[off + 1])} non-finite outputs -- an activation left the fp16 "
+                                      "hi/lo range (|x| >= 1023) or the inputs were non-finite")
+        return int(h[0]), (self.prefilter_tau > 0.0 and int(h[1]) != 0)
 
     def _redo_exact(self, fn, *args):
         """Repeats the forward with the prefilter off (exact by construction) and widens tau for the following calls:
@@ -440,7 +463,8 @@ class B200IDRNetwork(nn.Module):
         surface_mask = network_object_mask & object_mask
         idx = surface_mask.nonzero(as_tuple=False).squeeze(1)            # data-dependent size: one host sync, as in the reference
         M = idx.shape[0]
-        if self._screening_failed():
+        _, failed = self._host_checks(sdf_net, rend_net, torch.zeros(1, dtype=torch.int32, device=dev))
+        if failed:
             return self._redo_exact(self._forward_autograd, input, train_progress, steps01, eik_points, dsurf_rand)
         x_s, t_s, d_s = points[idx], dists[idx].unsqueeze(-1), ray_dirs[idx]
         c_s = cam_loc.unsqueeze(1).expand(B, N, 3).reshape(-1, 3)[idx]
@@ -537,8 +561,9 @@ class B200IDRNetwork(nn.Module):
                                       _lib.ptr(ws), _lib.ptr(sdf_out), _lib.ptr(rgb_values), _lib.ptr(surf_pts),
                                       _lib.ptr(normals), _lib.ptr(surf_head), _lib.ptr(hit_index), _lib.ptr(hit_offsets),
                                       stream))
-        M = int(hit_offsets[B].item())          # the single host sync: diff_surf_pts has a data-dependent shape
-        if self._screening_failed():
+        # the single host sync: diff_surf_pts has a data-dependent shape (+ guard and range monitors in the same read)
+        M, failed = self._host_checks(sdf_net, rend_net, hit_offsets[B])
+        if failed:
             return self._redo_exact(self._forward_native, input, train_progress, steps01, eik_points, dsurf_rand)
         diff_surf_pts = surf_pts[:M]
         output = {

@@ -41,6 +41,7 @@ class PackedNet:
             raise _lib.MvsdfError(L.mvsdf_last_error().decode())
         self.n_layers = L.mvsdf_net_num_layers(self.handle)
         self.nbytes = L.mvsdf_net_packed_bytes(self.handle)
+        self.status_off = L.mvsdf_net_status_offset(self.handle)
         self.blob: Optional[torch.Tensor] = None
 
     def __del__(self):
@@ -64,6 +65,20 @@ class PackedNet:
         _lib.check(_lib.lib().mvsdf_pack_weights(self.handle, _lib.ptr_array(vs), _lib.ptr_array(gs),
                                                  _lib.ptr_array(bs), _lib.ptr(self.blob), _stream(dev)))
         return self
+
+    def status(self) -> torch.Tensor:
+        """int32 view [4] of the blob's range monitors (include/mvsdf_b200.h MVSDF_STATUS_*); device tensor, no sync."""
+        return self.blob[self.status_off:self.status_off + 16].view(torch.int32)
+
+    def check_status(self):
+        """Host read (synchronises) of the range monitors; raises when the fp16 hi/lo representation was exceeded."""
+        st = self.status().cpu()
+        if int(st[0]) != 0:
+            raise _lib.MvsdfError(f"{self.kind} net: {int(st[0])} packed weight elements have |64*W| beyond the fp16 range "
+                                  "(|W| >= 1023.5 or non-finite): this network cannot be evaluated with the fp16 hi/lo split")
+        if int(st[1]) != 0:
+            raise _lib.MvsdfError(f"{self.kind} net: {int(st[1])} non-finite outputs since the last pack -- an activation "
+                                  "left the fp16 hi/lo range (|x| >= 1023) or the inputs were non-finite")
 
     def pack_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str, device):
         vs, gs, bs = [], [], []

@@ -21,15 +21,49 @@ def shard_bounds(n_pixels: int, rank: int, world: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def shard_rays(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
-    """Per-image ray slices for this rank; everything that is not per-ray is replicated."""
+def shard_index(n_pixels: int, rank: int, world: int, tile: int = 0) -> torch.Tensor:
+    """Ray indices (within one image) owned by `rank`.  tile = 0: one contiguous range (shard_bounds).  tile > 0: ray tiles
+    of `tile` consecutive rays dealt round-robin (tile j goes to rank j % world) -- SURVEY.md section 8e's remedy for load
+    imbalance: the hit fraction and the sphere-tracing iteration count vary across the image (the object sits in the
+    middle rows), so contiguous ranges give the outer ranks mostly sphere-miss rays."""
+    if tile <= 0:
+        b, e = shard_bounds(n_pixels, rank, world)
+        return torch.arange(b, e)
+    idx = torch.arange(n_pixels)
+    return idx[(idx // tile) % world == rank]
+
+
+def shard_rays(batch: Dict[str, torch.Tensor], rank: int, world: int, tile: int = 0) -> Dict[str, torch.Tensor]:
+    """Per-image ray slices for this rank (contiguous, or round-robin tiles when tile > 0); everything that is not
+    per-ray is replicated."""
     n = batch["uv"].shape[1]
-    b, e = shard_bounds(n, rank, world)
     out = dict(batch)
+    if tile <= 0:
+        b, e = shard_bounds(n, rank, world)
+        for k in RAY_KEYS:
+            if k in batch:
+                out[k] = batch[k][:, b:e].contiguous()
+        return out
+    idx = shard_index(n, rank, world, tile)
     for k in RAY_KEYS:
         if k in batch:
-            out[k] = batch[k][:, b:e].contiguous()
+            out[k] = batch[k][:, idx].contiguous()
     return out
+
+
+def mean_from_partials(local_sum: torch.Tensor, count: int, reduce_fn=None) -> torch.Tensor:
+    """Mean of a per-sample term whose samples are spread over the ranks: (sum over ALL ranks) / (count over ALL ranks).
+    The VALUE is the global mean on every rank; the GRADIENT is d(local_sum) / global_count, so that summing the parameter
+    gradients over the ranks (allreduce_gradients) gives exactly the single-GPU gradient.  reduce_fn = None: plain local
+    mean.  Used for the eikonal and surface-indicator terms (loss.py:30-35, :167-174), which the reference forms with
+    .mean() over tensors that are sharded here."""
+    if reduce_fn is None:
+        return local_sum / max(count, 1)
+    part = torch.stack([local_sum.detach().to(torch.float64),
+                        torch.tensor(float(count), dtype=torch.float64, device=local_sum.device)])
+    reduce_fn(part)
+    tot, cnt = part[0].to(local_sum.dtype), part[1].clamp_min(1.0).to(local_sum.dtype)
+    return (local_sum - local_sum.detach() + tot) / cnt
 
 
 def allreduce_partials(*partials: torch.Tensor, group=None) -> None:
@@ -59,7 +93,8 @@ def finalize_feat(partials: torch.Tensor) -> torch.Tensor:
 def allreduce_gradients(params, world_size: int = None, group=None) -> None:
     """Data-parallel training (outside the north-star forward metric): after ``loss.backward()`` every
     rank holds the gradient of ITS rays' share of the loss.  With the loss partials all-reduced before the scalars are
-    formed (``hot_path_losses(reduce_fn=...)``) each rank's backward already uses the GLOBAL denominators, so the global
+    formed (``B200IDRLoss.forward(reduce_fn=...)``: rgb, feature, depth AND -- through mean_from_partials -- the eikonal and
+    surface-indicator means) each rank's backward already uses the GLOBAL denominators, so the global
     gradient is the SUM over ranks -- one all-reduce over a single flat fp32 bucket (2.9 M floats for the 8x512 + 4x512
     networks: latency-bound over NVLink, no bucketing needed).  Parameters without a gradient contribute zeros so that
     all ranks build the same bucket."""

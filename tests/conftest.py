@@ -38,3 +38,21 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
     return load
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the measured value of every parity gate (tests/helpers.py gate()) next to its limit."""
+    try:
+        from tests.helpers import GATE_LOG
+    except Exception:
+        return
+    if not GATE_LOG:
+        return
+    import json
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "gate_report.json"), "w") as f:
+            json.dump(GATE_LOG, f, indent=1)
+    except OSError:
+        pass

@@ -8,8 +8,13 @@ from mvsdf_b200 import synth
 from mvsdf_b200.loss import B200IDRLoss
 from mvsdf_b200.network import B200IDRNetwork, default_conf
 from oracle import mvsdf_oracle as O
+from tests.helpers import gate
 
 pytestmark = pytest.mark.gpu
+
+# limits = ~3x the errors measured on the B200 (gpurun_out/gate_report.json)
+G_LOSS_REL = 1e-3
+G_PARAM_GRAD = 2e-2
 
 IN = ["uv", "pose", "intrinsics", "object_mask", "depths", "depth_cams", "center", "size"]
 GT = ["rgb", "feat", "cam", "feat_src", "src_cams", "size", "center", "depths", "depth_cams"]
@@ -53,8 +58,8 @@ def test_parameter_gradients_match_oracle_autograd(tp):
         pytest.skip("a discrete tracer decision flipped on this input; gradient comparison is not meaningful")
     ls = B200IDRLoss()(out, {k: scene[k].to(dev) for k in GT}, tp, 2)          # the call of idr_train.py:269
     for k in ("rgb_loss", "eikonal_loss", "depth_loss"):
-        assert abs(float(ls[k]) - float(rl[k])) < 1e-3 * max(1.0, abs(float(rl[k]))), k
-    assert abs(float(ls["loss"]) - float(ref_total)) < 1e-3 * abs(float(ref_total))
+        gate(k + "_rel", abs(float(ls[k]) - float(rl[k])) / max(1.0, abs(float(rl[k]))), G_LOSS_REL)
+    gate("total_loss_rel", abs(float(ls["loss"]) - float(ref_total)) / abs(float(ref_total)), G_LOSS_REL)
     ls["loss"].sum().backward()
     worst = 0.0
     for name, p in model.named_parameters():
@@ -63,8 +68,7 @@ def test_parameter_gradients_match_oracle_autograd(tp):
         scale = gr.abs().max().item() + 1e-8
         err = (p.grad.cpu() - gr).abs().max().item() / scale
         worst = max(worst, err)
-        assert err < 2e-2, f"{name}: relative gradient error {err:.3e}"
-    print(f"tp={tp}: worst relative parameter-gradient error {worst:.2e}")
+    gate("param_grad_rel_of_max", worst, G_PARAM_GRAD)
 
 
 def test_no_grad_training_forward_keeps_native_path():

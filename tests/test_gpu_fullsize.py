@@ -117,3 +117,65 @@ def test_cfg5_shaped_1080p_12_views_runs_and_is_order_invariant():
     for k in ("rgb_loss", "feat_loss"):
         assert torch.isfinite(a[k])
         assert abs(float(a[k]) - float(b[k])) <= 1e-6 * max(1.0, abs(float(a[k]))), k
+
+
+# ---- value parity at the full-size configurations -----------------------------------------------------------------------
+# Rays are independent, so a random sub-sample of the full image is a legitimate unit for the CPU oracle: the GPU path is
+# run on the WHOLE image (1.92 M rays / 1080p), the sub-sample's rows are shown to be bit-identical to a GPU run over the
+# sub-sample alone, and that run is compared value by value with oracle.idr_forward + hot_path_losses on exactly those rays
+# (same cameras, same 600x800 / 540x960 feature maps, same weights).
+def _subsample_parity(model, scene, dev, n_sub, seed, full_out=None):
+    from mvsdf_b200.loss import B200IDRLoss
+    from oracle import mvsdf_oracle as O
+    from tests.helpers import gate
+    N = scene["uv"].shape[1]
+    idx = torch.randperm(N, generator=torch.Generator().manual_seed(seed))[:n_sub].sort().values
+    sub = dict(scene)
+    for k in ("uv", "object_mask", "rgb"):
+        sub[k] = scene[k][:, idx].contiguous()
+    out = model({k: sub[k].to(dev) for k in IN_KEYS})
+    losses = B200IDRLoss().hot_path_losses(out, {k: sub[k].to(dev) for k in GT_KEYS}, 0.5)
+    if full_out is not None:       # the sub-sample run IS the full-size run restricted to these rays
+        for k in ("points", "rgb_values", "sdf_output", "network_object_mask"):
+            assert _same(full_out[k][idx.to(dev)], out[k]), f"{k}: sub-sample run differs from the full-image run"
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), sub, None, False)
+        ref_l = O.hot_path_losses(ref, sub, 0.5)
+    nm, rm = out["network_object_mask"].cpu(), ref["network_object_mask"]
+    flips = int((nm != rm).sum())
+    print(f"sub-sample of {n_sub} rays: {flips} hit-mask flips, {int(rm.sum())} hits")
+    gate("hit_mask_flip_frac", flips / n_sub, 1e-3)
+    both = nm & rm
+    cam = scene["pose"][0, :3, 3]
+    d_ref = (ref["points"] - cam).norm(dim=1)[both]
+    d_new = (out["points"].cpu() - cam).norm(dim=1)[both]
+    rel = (d_new - d_ref).abs() / d_ref
+    gate("depth_rel_frac_above_1e-4", (rel > 1e-4).float().mean().item(), 0.01, f"(max {rel.max():.2e})")
+    gate("depth_rel_median", rel.median().item(), 2e-5)
+    rgb_err = (out["rgb_values"].cpu() - ref["rgb_values"]).abs().max(dim=1).values[both]
+    gate("rgb_abs_median", rgb_err.median().item(), 1e-4)
+    gate("rgb_abs_frac_above_1e-3", (rgb_err > 1e-3).float().mean().item(), 0.01, f"(max {rgb_err.max():.2e})")
+    if flips == 0:
+        gate("diff_surf_pts_abs_max", (out["diff_surf_pts"].cpu() - ref["diff_surf_pts"]).abs().max().item(), 5e-4)
+        gate("rgb_loss_rel", abs(float(losses["rgb_loss"]) - float(ref_l["rgb_loss"])) / abs(float(ref_l["rgb_loss"])), 1e-3)
+        gate("feat_loss_rel", abs(float(losses["feat_loss"]) - float(ref_l["feat_loss"])) / abs(float(ref_l["feat_loss"])), 2e-2)
+    else:
+        gate("rgb_loss_abs", abs(float(losses["rgb_loss"]) - float(ref_l["rgb_loss"])), 5e-3)
+
+
+def test_cfg2_random_subsample_matches_cpu_oracle(cfg2):
+    model, scene, dev = cfg2
+    full_out = model({k: scene[k].to(dev) for k in IN_KEYS})
+    _subsample_parity(model, scene, dev, 4096, seed=11, full_out=full_out)
+
+
+def test_cfg5_random_subsample_matches_cpu_oracle():
+    """1080p, 12 source views (BASELINE.json configs[4]): 2 048 random rays of the full image against the CPU oracle."""
+    from mvsdf_b200.network import B200IDRNetwork, default_conf
+    dev = torch.device("cuda:0")
+    scene = synth.make_scene(1080, 1920, n_images=1, n_src=12, seed=1)
+    model = B200IDRNetwork(default_conf(512)).to(dev)
+    model.load_state_dict(synth.make_state_dict(**CFG2_WEIGHTS))
+    model.eval()
+    _subsample_parity(model, scene, dev, 2048, seed=12)

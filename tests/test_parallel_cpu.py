@@ -65,6 +65,18 @@ def test_two_rank_loss_reduction_matches_unsharded():
     assert abs(ret["feat"] - float(ref["feat_loss"])) < 1e-6
 
 
+def _train_loss(out, rgb_gt, loss_mod, reduce_fn, n_total):
+    """rgb (global denominator) + eikonal + surface-indicator terms of IDRLoss.forward with the reference's weights
+    (loss.py:176-219); the eikonal / surface means go through B200IDRLoss's own partial reducers."""
+    from mvsdf_b200 import conf
+    m = out["network_object_mask"] & out["object_mask"]
+    rgb = (out["rgb_values"][m] - rgb_gt.reshape(-1, 3)[m]).abs().sum() / n_total
+    eik = loss_mod.get_eikonal_loss(out["grad_theta"], reduce_fn=reduce_fn)
+    surf = loss_mod.get_surf_loss(out["surf_indicator_output"], out["network_object_mask"], out["object_mask_true"],
+                                  reduce_fn=reduce_fn)
+    return conf.rgb_weight(0.5) * rgb + conf.eikonal_weight * eik + conf.surf_weight * surf, eik, surf
+
+
 def _grad_worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -72,28 +84,44 @@ def _grad_worker(rank, world, port, ret):
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mvsdf_b200 import parallel, synth
+    from mvsdf_b200.loss import B200IDRLoss
     from oracle import mvsdf_oracle as O
     sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     scene = synth.make_scene(20, 20, n_images=2, n_src=2, seed=6)
-    part = parallel.shard_rays(scene, rank, world)
-    out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), part, None, False)
-    m = out["network_object_mask"] & out["object_mask"]
-    # this rank's share of the rgb loss with the GLOBAL denominator (all rays of all ranks), as after the partial all-reduce
+    tile = 16                                             # round-robin ray tiles, like bench.py's strong-scaling split
+    part = parallel.shard_rays(scene, rank, world, tile=tile)
     n_total = scene["uv"].shape[0] * scene["uv"].shape[1]
-    loss = (out["rgb_values"][m] - part["rgb"].reshape(-1, 3)[m]).abs().sum() / n_total
+    eik_all = torch.rand(n_total // 2, 3, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    # eikonal samples split over the ranks in proportion to their rays: rank r draws R_r / 2 of them
+    n_loc = [sum(int(parallel.shard_index(scene["uv"].shape[1], r, world, tile).numel()) for _ in range(scene["uv"].shape[0])) // 2
+             for r in range(world)]
+    b = sum(n_loc[:rank])
+    e = b + n_loc[rank]
+    out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), part, 0.5, True, eik_points=eik_all[b:e],
+                        skip_min_sdf=True)
+    loss, eik, surf = _train_loss(out, part["rgb"], B200IDRLoss(), parallel.allreduce_partials, n_total)
     loss.backward()
     plist = list(params.values())
     parallel.allreduce_gradients(plist)
     if rank == 0:
         ret["grads"] = {k: (p.grad.clone() if p.grad is not None else None) for k, p in params.items()}
+        ret["eik"], ret["surf"] = float(eik), float(surf)
     dist.destroy_process_group()
 
 
 def test_two_rank_gradient_allreduce_matches_unsharded_backward():
+    """Sharded training step (rgb + eikonal + surface-indicator terms, rays dealt in round-robin tiles, eikonal samples
+    split) followed by allreduce_gradients == the unsharded backward: every term must be formed with GLOBAL denominators
+    (local .mean()s of the eikonal / surface terms would be over-weighted by world_size)."""
     sys.path.insert(0, ROOT)
-    from mvsdf_b200 import synth
+    from mvsdf_b200 import parallel, synth
+    from mvsdf_b200.loss import B200IDRLoss
     from oracle import mvsdf_oracle as O
+    # round-robin tiles cover every ray exactly once
+    for n, w, tile in [(400, 2, 16), (4096, 8, 256), (1000, 3, 7)]:
+        covered = sorted(int(i) for r in range(w) for i in parallel.shard_index(n, r, w, tile))
+        assert covered == list(range(n))
     mgr = mp.Manager()
     ret = mgr.dict()
     port = 31500 + (os.getpid() % 2000)
@@ -101,16 +129,20 @@ def test_two_rank_gradient_allreduce_matches_unsharded_backward():
     sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     scene = synth.make_scene(20, 20, n_images=2, n_src=2, seed=6)
-    out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), scene, None, False)
-    m = out["network_object_mask"] & out["object_mask"]
-    loss = (out["rgb_values"][m] - scene["rgb"].reshape(-1, 3)[m]).abs().sum() / m.numel()
+    n_total = scene["uv"].shape[0] * scene["uv"].shape[1]
+    eik_all = torch.rand(n_total // 2, 3, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), scene, 0.5, True, eik_points=eik_all,
+                        skip_min_sdf=True)
+    loss, eik, surf = _train_loss(out, scene["rgb"], B200IDRLoss(), None, n_total)
     loss.backward()
+    assert abs(ret["eik"] - float(eik)) < 1e-6 * max(1.0, abs(float(eik)))
+    assert abs(ret["surf"] - float(surf)) < 1e-6
     checked = 0
     for k, p in params.items():
         g = ret["grads"][k]
         if p.grad is None:
             assert g is None or float(g.abs().max()) == 0.0
             continue
-        assert torch.allclose(g, p.grad, rtol=1e-4, atol=1e-7), k
+        assert torch.allclose(g, p.grad, rtol=2e-4, atol=1e-7), (k, (g - p.grad).abs().max())
         checked += 1
     assert checked >= 20
