@@ -218,6 +218,53 @@ int mvsdf_rgb_l1_partials(const float* rgb_values, const float* rgb_gt, const ui
                           double* partials, void* stream);
 int mvsdf_rgb_l1_finalize(const double* partials, float* out_loss, void* stream);
 
+/* ---- the training step: backward through the two MLPs + optimiser --------------------------
+ * What eager autograd does in the reference: loss.backward() (code/training/idr_train.py:287) through
+ * ImplicitNetwork.forward / .gradient -- second order, create_graph=True (implicit_differentiable_renderer.py:96-107) --
+ * and RenderingNetwork.forward (:145-167), torch.nn.utils.clip_grad_norm_ (:292) and torch.optim.Adam.step (:300).
+ *
+ * Protocol per step:  mvsdf_pack_weights (+ mvsdf_pack_weights_t: W^T tiles for the reverse sweep)
+ *   -> mvsdf_sdf_forward_train / mvsdf_render_forward_train: the fused forward kernels, which additionally write the input
+ *      operand of every layer (fp16 hi/lo, mvsdf_train_save_bytes) -- everything the backward needs: with softplus(beta=100),
+ *      sp'(z) = 1 - exp(-100 sp(z)) and sp''(z) S = 100 (1 - sp'(z)) T are functions of the saved values
+ *   -> mvsdf_sdf_backward / mvsdf_render_backward: reverse sweep on the tcgen05 tile core (D = W^T [dZ | dS], epilogue applies
+ *      sp' / sp'' or ReLU', chains the positional encoding into d/dx) and the dW GEMM over the points; results in PLAN
+ *      coordinates: out_dw [mvsdf_train_dw_floats] = per layer [padded out rows, padded in], out_db [mvsdf_train_db_floats]
+ *   -> mvsdf_weight_grads: weight-norm chain  dg = <dW, v^>,  dv = g/||v|| (dW - <dW, v^> v^)  into tensors shaped like the
+ *      parameters (weight_v [out,in], weight_g [out,1], bias [out])
+ *   -> mvsdf_adam_step.
+ * with_grad = 1: value + d/dx columns (SDF net, 16 points per tile), 0: plain columns (rendering net, 64 points per tile). */
+size_t mvsdf_train_packed_t_bytes(const mvsdf_net* net);
+size_t mvsdf_train_save_bytes(const mvsdf_net* net, int64_t n, int with_grad);
+size_t mvsdf_train_workspace_bytes(const mvsdf_net* net, int64_t n, int with_grad);
+size_t mvsdf_train_dw_floats(const mvsdf_net* net);
+size_t mvsdf_train_db_floats(const mvsdf_net* net);
+int mvsdf_pack_weights_t(const mvsdf_net* net, const float* const* weight_v_host, const float* const* weight_g_host, void* packed_t,
+                         void* stream);
+/* ImplicitNetwork.forward + .gradient, full head: out_full [n, 2+F], out_grad [n,3]; save [save_bytes]. */
+int mvsdf_sdf_forward_train(const mvsdf_net* net, const void* packed, const float* x, int64_t n, size_t save_bytes, void* save,
+                            float* out_full, float* out_grad, void* stream);
+/* g_full [n, 2+F] = dL/d full, g_grad [n,3] = dL/d grad (either may be NULL = zero); out_dx [n,3] optional = dL/dx. */
+int mvsdf_sdf_backward(const mvsdf_net* net, const void* packed_t, const float* x, int64_t n, const void* save, const float* g_full,
+                       const float* g_grad, size_t workspace_bytes, void* workspace, float* out_dx, float* out_dw, float* out_db,
+                       void* stream);
+int mvsdf_render_forward_train(const mvsdf_net* net, const void* packed, const float* points, const float* view_dirs,
+                               const float* normals, const float* features, int64_t n, size_t save_bytes, void* save, float* out_rgb,
+                               void* stream);
+/* rgb [n,3] = the forward output (tanh'), g_rgb [n,3] = dL/d rgb; d_points / d_normals [n,3], d_feats [n,F] optional. */
+int mvsdf_render_backward(const mvsdf_net* net, const void* packed_t, int64_t n, const void* save, const float* rgb, const float* g_rgb,
+                          size_t workspace_bytes, void* workspace, float* d_points, float* d_normals, float* d_feats, float* out_dw,
+                          float* out_db, void* stream);
+/* *_host: HOST arrays of device pointers, one per source layer lin{l} (like mvsdf_pack_weights). */
+int mvsdf_weight_grads(const mvsdf_net* net, const float* dw, const float* db, const float* const* weight_v_host,
+                       const float* const* weight_g_host, float* const* out_dv_host, float* const* out_dg_host,
+                       float* const* out_dbias_host, void* stream);
+/* torch.optim.Adam.step over n_tensors fp32 tensors with clip_grad_norm_(max_grad_norm) folded in (<= 0: no clipping);
+ * step = 1, 2, ...; scratch_sumsq: device double; out_grad_norm: optional device float = ||g|| before clipping. */
+int mvsdf_adam_step(int n_tensors, float* const* params_host, const float* const* grads_host, float* const* exp_avg_host,
+                    float* const* exp_avg_sq_host, const int64_t* sizes_host, float lr, float beta1, float beta2, float eps, int step,
+                    float max_grad_norm, double* scratch_sumsq, float* out_grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

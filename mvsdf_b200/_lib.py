@@ -52,6 +52,28 @@ def _declare(lib):
     lib.mvsdf_sdf_value_grad.argtypes = [P, P, P, c_int64, P, c_int, P, P, P, P]
     lib.mvsdf_render_forward.restype = c_int
     lib.mvsdf_render_forward.argtypes = [P, P, P, P, P, P, c_int64, P, P, P]
+    # ---- training step (csrc/train_abi.cu)
+    for name in ("mvsdf_train_packed_t_bytes", "mvsdf_train_dw_floats", "mvsdf_train_db_floats"):
+        getattr(lib, name).restype = c_size_t
+        getattr(lib, name).argtypes = [P]
+    for name in ("mvsdf_train_save_bytes", "mvsdf_train_workspace_bytes"):
+        getattr(lib, name).restype = c_size_t
+        getattr(lib, name).argtypes = [P, c_int64, c_int]
+    lib.mvsdf_pack_weights_t.restype = c_int
+    lib.mvsdf_pack_weights_t.argtypes = [P, POINTER(P), POINTER(P), P, P]
+    lib.mvsdf_sdf_forward_train.restype = c_int
+    lib.mvsdf_sdf_forward_train.argtypes = [P, P, P, c_int64, c_size_t, P, P, P, P]
+    lib.mvsdf_sdf_backward.restype = c_int
+    lib.mvsdf_sdf_backward.argtypes = [P, P, P, c_int64, P, P, P, c_size_t, P, P, P, P, P]
+    lib.mvsdf_render_forward_train.restype = c_int
+    lib.mvsdf_render_forward_train.argtypes = [P, P, P, P, P, P, c_int64, c_size_t, P, P, P]
+    lib.mvsdf_render_backward.restype = c_int
+    lib.mvsdf_render_backward.argtypes = [P, P, c_int64, P, P, P, c_size_t, P, P, P, P, P, P, P]
+    lib.mvsdf_weight_grads.restype = c_int
+    lib.mvsdf_weight_grads.argtypes = [P, P, P, POINTER(P), POINTER(P), POINTER(P), POINTER(P), POINTER(P), P]
+    lib.mvsdf_adam_step.restype = c_int
+    lib.mvsdf_adam_step.argtypes = [c_int, POINTER(P), POINTER(P), POINTER(P), POINTER(P), POINTER(c_int64), c_float, c_float, c_float,
+                                    c_float, c_int, c_float, P, P, P]
     class TracerParams(ctypes.Structure):
         _fields_ = [("object_bounding_sphere", c_float), ("sdf_threshold", c_float), ("line_search_step", c_float),
                     ("dist_clip", c_float), ("line_step_iters", c_int), ("sphere_tracing_iters", c_int),

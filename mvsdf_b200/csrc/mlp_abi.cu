@@ -14,10 +14,6 @@
 #include "internal.h"
 #include "mlp_pair2_kernel.cuh"
 
-struct mvsdf_net {
-  mvsdf::NetPlan plan;
-};
-
 namespace mvsdf {
 
 thread_local char g_err[512] = "";
@@ -154,7 +150,7 @@ __global__ void pack_layer_kernel(const float* __restrict__ v, const float* __re
 
 static unsigned long long* g_trace = nullptr;
 
-static int fill_args(const NetPlan& p, const void* packed, int head, MlpArgs& a) {
+int fill_mlp_args(const NetPlan& p, const void* packed, int head, MlpArgs& a) {
   memset(&a, 0, sizeof(a));
   a.trace = g_trace;
   a.packed = static_cast<const uint8_t*>(packed);
@@ -254,6 +250,7 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   const long long tiles = (n + per_tile - 1) / per_tile;
   if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
   // small host-known batches cannot fill clusters: fall back to single-CTA scheduling (same kernel, CL = 1)
+  if (a.save) return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, false, st);      // training forward: the kernel that saves
   const bool small = n_dev == nullptr && tiles < 2 * sm_count();
   // 1 = split-K pipelined CTA-pair kernel (default), 0 = single-CTA kernel (A/B runs)
   static const int pair = env_int("MVSDF_PAIR", 1);
@@ -264,7 +261,8 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
 }
 
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,
-            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st, bool screening) {
+            float* out_sdf, float* out_full, float* out_grad, bool with_grad, cudaStream_t st, bool screening, uint8_t* save,
+            const long long* save_off) {
   if (!net || net->plan.kind != NET_SDF) return fail(MVSDF_ERR_INVALID, "expected an SDF net plan");
   if (n == 0 && !n_dev) return MVSDF_OK;   // empty batch: nothing to enqueue
   if (!packed || (!x && n > 0) || n < 0) return fail(MVSDF_ERR_INVALID, "null pointer / negative count");
@@ -273,29 +271,40 @@ int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n,
   if (head == HEAD_FULL && !out_full) return fail(MVSDF_ERR_INVALID, "out_full is required for the full head");
   if (with_grad && !out_grad) return fail(MVSDF_ERR_INVALID, "out_grad is required");
   MlpArgs a;
-  fill_args(net->plan, packed, head, a);
+  fill_mlp_args(net->plan, packed, head, a);
   a.x = x;
   a.out_sdf = out_sdf;
   a.out_full = out_full;
   a.out_grad = out_grad;
   a.lp = (screening && !with_grad && head == HEAD_SDF_ONLY) ? 1 : 0;
+  if (save) {
+    if (n_dev) return fail(MVSDF_ERR_INVALID, "the saving forward needs a host-side count");
+    a.save = save;
+    for (int l = 0; l < kMaxLayers; ++l) a.save_off[l] = save_off[l];
+  }
   return with_grad ? launch_mlp<NET_SDF, 1>(net->plan, a, n, n_dev, st) : launch_mlp<NET_SDF, 0>(net->plan, a, n, n_dev, st);
 }
 
 int mlp_render(const mvsdf_net* net, const void* packed, const float* pts, const float* view, const float* normals,
-               const float* feats, int feat_stride, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st) {
+               const float* feats, int feat_stride, int64_t n, const int32_t* n_dev, float* rgb, cudaStream_t st, uint8_t* save,
+               const long long* save_off) {
   if (!net || net->plan.kind != NET_RENDER) return fail(MVSDF_ERR_INVALID, "expected a rendering net plan");
   if (n == 0 && !n_dev) return MVSDF_OK;
   if (!packed || n < 0 || !rgb || ((!pts || !view || !normals || !feats) && n > 0))
     return fail(MVSDF_ERR_INVALID, "null pointer / negative count");
   MlpArgs a;
-  fill_args(net->plan, packed, HEAD_FULL, a);
+  fill_mlp_args(net->plan, packed, HEAD_FULL, a);
   a.x = pts;
   a.view = view;
   a.normals = normals;
   a.feats = feats;
   a.feat_stride = feat_stride > 0 ? feat_stride : net->plan.feat_size;
   a.out_rgb = rgb;
+  if (save) {
+    if (n_dev) return fail(MVSDF_ERR_INVALID, "the saving forward needs a host-side count");
+    a.save = save;
+    for (int l = 0; l < kMaxLayers; ++l) a.save_off[l] = save_off[l];
+  }
   return launch_mlp<NET_RENDER, 0>(net->plan, a, n, n_dev, st);
 }
 

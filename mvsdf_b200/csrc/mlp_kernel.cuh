@@ -63,6 +63,11 @@ struct MlpArgs {
   float* out_grad;           // [n,3]          (value+gradient mode)
   float* out_rgb;            // [n,3]          (render)
   int* status;               // packed blob's status words (netplan.h kStatus*)
+  // training forward (single-CTA kernel only): the input operand of every layer is also written to global memory for the
+  // native backward (mlp_bwd_kernel.cuh).  save_off[l] = byte offset of the image of layer l's input inside `save`;
+  // layout per layer: [tile][16-column slice][8-feature block][hi 2x128 B | lo 2x128 B] (save_addr below).
+  uint8_t* save;
+  long long save_off[kMaxLayers];
   unsigned long long* trace; // debug only: clock64 timeline of pair 0 (tools/diag_trace.py); nullptr in production
   LayerPlan L[10];
 };
@@ -74,14 +79,26 @@ __host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
 // Range monitor: activations are stored as fp16 hi/lo of kActScale * x, so |x| >= 1023 overflows to inf; the split then
 // yields NaN (inf - inf), which poisons every accumulator of that column and surfaces at the head.  Checking the values
 // the head writes therefore catches any overflow on the way at the cost of one predicate per OUTPUT element.
-__device__ __forceinline__ float checked(float v, int* status) {
-  if (!(fabsf(v) <= 3.0e38f) && status) atomicAdd(status + kStatusNonFinite, 1);
+// (The ReLU of the rendering net is the exception -- fmaxf(NaN, 0) = 0 swallows the NaN -- so its pre-activations are
+// checked too, and so is anything beyond the fp16 range on its way into the split: limit = 65504 / kActScale.)
+__device__ __forceinline__ float checked(float v, int* status, float limit = 3.0e38f) {
+  if (!(fabsf(v) <= limit) && status) atomicAdd(status + kStatusNonFinite, 1);
   return v;
 }
+constexpr float kActLimit = 65504.0f / kActScale;
 
 // byte offset of (column n, feature k) inside an activation operand buffer
 __device__ __forceinline__ uint32_t xoff(int n, int k) {
   return (uint32_t)((k >> 3) * kBCoreStride + (n >> 3) * 128 + (k & 7) * 16 + (n & 7) * 2);
+}
+
+// Saved-operand image ("K-sliced"): the same fp16 hi/lo pairs as the shared-memory operand, but grouped so that a 16-column
+// slice of ALL features is contiguous -- read along the columns it is a K-major UMMA operand (8 rows x 16 B core matrices,
+// LBO = 128, SBO = 512), which is what dW = dZ * H^T (contraction over the points) needs.  Byte offset of the 16-byte hi
+// vector of (feature f, columns [8 cb, 8 cb + 8)) inside the image of one 64-column tile with `kc` feature blocks; the lo
+// vector sits 256 B behind it.
+__device__ __forceinline__ size_t save_addr(int kc, int f, int cb) {
+  return (size_t)(cb >> 1) * (size_t)kc * 512 + (size_t)(f >> 3) * 512 + (size_t)(cb & 1) * 128 + (size_t)(f & 7) * 16;
 }
 
 __device__ __forceinline__ void store_split(uint32_t hi_addr, uint32_t lo_addr, float v) {
@@ -363,6 +380,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
           }
           const uint32_t o = xoff(col, k);
           store_split(s_pehi + o, s_pelo + o, v * kActScale);
+          if (a.save) {
+            const __half h = __float2half_rn(v * kActScale);
+            const __half lo = __float2half_rn(v * kActScale - __half2float(h));
+            uint8_t* g = a.save + a.save_off[0] + (size_t)tile * (kPeCores * kBCoreStride) + save_addr(kPeCores, k, col >> 3) + (col & 7) * 2;
+            *reinterpret_cast<__half*>(g) = h;
+            *reinterpret_cast<__half*>(g + 256) = lo;
+          }
         }
       } else {
         // render input [points(3), PE4(view)(27), normals(3), features(F)]  (implicit_differentiable_renderer.py:150)
@@ -399,6 +423,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
           }
           const uint32_t o = xoff(col, k);
           store_split(s_xhi + o, s_xlo + o, v * kActScale);
+          if (a.save) {
+            const int kc0 = kpad >> 3;
+            const __half h = __float2half_rn(v * kActScale);
+            const __half lo = __float2half_rn(v * kActScale - __half2float(h));
+            uint8_t* g = a.save + a.save_off[0] + (size_t)tile * ((size_t)kc0 * kBCoreStride) + save_addr(kc0, k, col >> 3) + (col & 7) * 2;
+            *reinterpret_cast<__half*>(g) = h;
+            *reinterpret_cast<__half*>(g + 256) = lo;
+          }
         }
       }
       ptx::tc_fence_before();
@@ -437,6 +469,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
                 for (int i = 0; i < 8; ++i) {
                   const float z0 = fmaf(__uint_as_float(v[2 * i]), kInvScale, bias);
                   const float z1 = fmaf(__uint_as_float(v[2 * i + 1]), kInvScale, bias);
+                  if (KIND == NET_RENDER) {       // fmaxf(NaN, 0) = 0 would swallow an overflow of the previous layer
+                    checked(z0, a.status, kActLimit);
+                    checked(z1, a.status, kActLimit);
+                  }
                   const float y0 = (KIND == NET_SDF) ? softplus100_scaled(z0) : fmaxf(z0, 0.0f) * kActScale;
                   const float y1 = (KIND == NET_SDF) ? softplus100_scaled(z1) : fmaxf(z1, 0.0f) * kActScale;
                   pack_split(y0, y1, phi[m][i], plo[m][i]);
@@ -496,6 +532,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
             if (m < lp.m_tiles) {
               const int f = m * kTileM + row;
               const uint32_t o0 = xoff(cg * 16, f);          // my 16 columns = two 16-byte vectors (8 columns each)
+              const int kc_next = a.L[l + 1].k_chunks * (kChunkK / 8);
+              uint8_t* gsave = (a.save && f < kc_next * 8)
+                                   ? a.save + a.save_off[l + 1] + (size_t)tile * ((size_t)kc_next * kBCoreStride) + save_addr(kc_next, f, cg * 2)
+                                   : nullptr;
               if (skip_src && f >= a.skip_rows_begin) {
                 // rows that hold the skip connection: copy PE (already scaled & split) instead of softplus
                 const int k = f - a.skip_rows_begin;
@@ -510,12 +550,20 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
                   }
                   ptx::st_shared_v4(s_xhi + o0 + j * 128, vh.x, vh.y, vh.z, vh.w);
                   ptx::st_shared_v4(s_xlo + o0 + j * 128, vl.x, vl.y, vl.z, vl.w);
+                  if (gsave) {
+                    *reinterpret_cast<uint4*>(gsave + j * 128) = vh;
+                    *reinterpret_cast<uint4*>(gsave + 256 + j * 128) = vl;
+                  }
                 }
               } else {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                   ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[m][4 * j], phi[m][4 * j + 1], phi[m][4 * j + 2], phi[m][4 * j + 3]);
                   ptx::st_shared_v4(s_xlo + o0 + j * 128, plo[m][4 * j], plo[m][4 * j + 1], plo[m][4 * j + 2], plo[m][4 * j + 3]);
+                  if (gsave) {
+                    *reinterpret_cast<uint4*>(gsave + j * 128) = make_uint4(phi[m][4 * j], phi[m][4 * j + 1], phi[m][4 * j + 2], phi[m][4 * j + 3]);
+                    *reinterpret_cast<uint4*>(gsave + 256 + j * 128) = make_uint4(plo[m][4 * j], plo[m][4 * j + 1], plo[m][4 * j + 2], plo[m][4 * j + 3]);
+                  }
                 }
               }
             }

@@ -485,6 +485,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                     }
                     const float t0 = fmaf(__uint_as_float(va[hcol][2 * i]), kK, fmaf(__uint_as_float(vb[hcol][2 * i]), kK, bias_k));
                     const float t1 = fmaf(__uint_as_float(va[hcol][2 * i + 1]), kK, fmaf(__uint_as_float(vb[hcol][2 * i + 1]), kK, bias_k));
+                    if (KIND == NET_RENDER) {     // fmaxf(NaN, 0) = 0 would swallow an overflow; t = kActScale * z here
+                      checked(t0, a.status, 65504.0f);
+                      checked(t1, a.status, 65504.0f);
+                    }
                     const float y0 = (KIND == NET_SDF && !(P2_DEBUG & 8)) ? softplus_t_scaled(t0) : fmaxf(t0, 0.0f);
                     const float y1 = (KIND == NET_SDF && !(P2_DEBUG & 8)) ? softplus_t_scaled(t1) : fmaxf(t1, 0.0f);
                     pack_split_fh(y0, y1, phi[i], plo[i]);

@@ -470,7 +470,6 @@ class B200IDRNetwork(nn.Module):
         c_s = cam_loc.unsqueeze(1).expand(B, N, 3).reshape(-1, 3)[idx]
         sdf_p = [t for lin in self.implicit_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
         rend_p = [t for lin in self.rendering_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
-        skip_in = self.implicit_network.skip_in
 
         n_eik = R // 2
         if eik_points is None:
@@ -481,8 +480,9 @@ class B200IDRNetwork(nn.Module):
             ds_on, ds_jit = self.depth_surface_samples(input, n_eik, dsurf_rand)
             extra_pts = torch.cat([extra_pts, ds_on, ds_jit], dim=0).contiguous()
 
-        full_s, g_s = SdfEval.apply(sdf_net, skip_in, 6, x_s, *sdf_p)            # :202 restricted to the surface rays, :275
-        full_e, g_e = SdfEval.apply(sdf_net, skip_in, 6, extra_pts, *sdf_p)      # :256, :275
+        shared = {}     # the surface set is evaluated ONCE (the reference does it three times: :202, :325, :326)
+        full_s, g_s = SdfEval.apply(sdf_net, shared, x_s, *sdf_p)                # :202 restricted to the surface rays, :275
+        full_e, g_e = SdfEval.apply(sdf_net, None, extra_pts, *sdf_p)            # :256, :275
         f_s = full_s[:, :1]
         eik_pts = torch.cat([x_s, extra_pts], dim=0)
         keep = object_mask_true[idx]
@@ -490,14 +490,15 @@ class B200IDRNetwork(nn.Module):
         dot = (g_s.detach() * d_s).sum(-1, keepdim=True)
         x_diff = c_s + (t_s - (f_s - f_s.detach()) / dot) * d_s
         # get_rbg_value (:324-338)
-        full_d, n_d = SdfEval.apply(sdf_net, skip_in, 6, x_diff, *sdf_p)
+        # x_diff equals x_s in value (f_s - f_s.detach() = 0): same forward results, own node in the autograd graph
+        full_d, n_d = SdfEval.apply(sdf_net, shared, x_diff, *sdf_p)
         feats = full_d[:, 2:]
         p_in, n_in, v_in = x_diff, n_d, -d_s
         if train_progress < conf.phase[0] or conf.disable_rgb_grad:
             p_in, n_in, v_in = p_in.detach(), n_in.detach(), v_in.detach()
         rgb_values = torch.ones(R, 3, dtype=torch.float32, device=dev)
         if M > 0:
-            rgb_hit = RenderEval.apply(rend_net, 4, p_in, n_in, v_in, feats.contiguous(), *rend_p)
+            rgb_hit = RenderEval.apply(rend_net, p_in, n_in, v_in, feats.contiguous(), *rend_p)
             rgb_values = rgb_values.index_put((idx,), rgb_hit)
         counts = surface_mask.view(B, -1).sum(-1)
         hit_offsets = torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(torch.int32)

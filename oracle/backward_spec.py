@@ -68,9 +68,11 @@ def fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
 
 def sdf_value_grad_backward(x: torch.Tensor, vs: Sequence[torch.Tensor], gs: Sequence[torch.Tensor],
                             bs: Sequence[torch.Tensor], skip_in: Sequence[int], n_freqs: int, g_full: torch.Tensor,
-                            g_grad: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
+                            g_grad: torch.Tensor, trace: dict = None) -> Tuple[torch.Tensor, List[torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
     """x [P,3]; vs/gs/bs = weight_v [out,in] / weight_g [out,1] / bias [out] per layer; g_full [P, 2+F]; g_grad [P,3].
-    Returns (dx [P,3], [dv_l], [dg_l], [db_l])."""
+    Returns (dx [P,3], [dv_l], [dg_l], [db_l]).  `trace` (optional dict) receives the per-layer intermediates
+    H, T (layer inputs), DZ, DS (gradients w.r.t. the pre-activations) and DW (w.r.t. the folded weights) -- what the
+    kernels of csrc/mlp_bwd_kernel.cuh keep in their saved / dumped images (tools/diag_backward.py compares them)."""
     n = len(vs)
     W = [fold(v, g) for v, g in zip(vs, gs)]
     pe, dpe, d2pe = _pe_all(x, n_freqs)
@@ -99,7 +101,9 @@ def sdf_value_grad_backward(x: torch.Tensor, vs: Sequence[torch.Tensor], gs: Seq
     ds[:, 0, :] = g_grad
     d_pe = torch.zeros_like(pe)                               # gradient reaching the positional encoding (value path)
     d_dpe = torch.zeros_like(dpe)                             # ... and its Jacobian columns (tangent path)
+    DZ, DS = [None] * n, [None] * n
     for l in range(n - 1, -1, -1):
+        DZ[l], DS[l] = dz, ds
         dW[l] = dz.T @ H[l] + torch.einsum("poj,pij->oi", ds, T[l])
         db[l] = dz.sum(dim=0)
         dh = dz @ W[l]
@@ -118,6 +122,8 @@ def sdf_value_grad_backward(x: torch.Tensor, vs: Sequence[torch.Tensor], gs: Seq
             dz = _sp1(zp) * dh + _sp2(zp) * (S[l - 1] * dt).sum(dim=-1)
     # PE: feature d depends on coordinate c(d) only, so J^T and the second derivative are sums over features
     dx = torch.einsum("pd,pdj->pj", d_pe, dpe) + torch.einsum("pdj,pdj->pj", d_dpe, d2pe)
+    if trace is not None:
+        trace.update(H=H, T=T, DZ=DZ, DS=DS, DW=dW, DB=db)
     # ---------------- weight norm
     dv, dg = [], []
     for l in range(n):

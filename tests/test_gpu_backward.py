@@ -1,0 +1,124 @@
+"""GPU: the native backward of the two MLPs (csrc/mlp_bwd_kernel.cuh, csrc/train_abi.cu) against
+the explicit reverse chain of oracle/backward_spec.py in fp64 -- itself pinned to autograd through the oracle restatement
+of the reference (tests/test_backward_spec.py) -- and the fused Adam step against torch.optim.Adam + clip_grad_norm_.
+Everything goes through the C ABI (mvsdf_sdf_forward_train / _backward, mvsdf_render_*, mvsdf_weight_grads, mvsdf_adam_step)."""
+import pytest
+import torch
+
+from mvsdf_b200 import ops, synth
+from oracle import backward_spec as S
+from tests.helpers import gate
+
+pytestmark = pytest.mark.gpu
+
+# limits: fraction of the tensor's max |gradient|; fp16 hi/lo operands (22 bits), fp32 accumulation
+G_DX = 2e-4
+G_PARAM = 2e-4
+
+
+def _sdf_lists(sd, n_lin=9, dtype=torch.float64, device="cpu"):
+    vs = [sd[f"implicit_network.lin{l}.weight_v"].to(device=device, dtype=dtype) for l in range(n_lin)]
+    gs = [sd[f"implicit_network.lin{l}.weight_g"].to(device=device, dtype=dtype) for l in range(n_lin)]
+    bs = [sd[f"implicit_network.lin{l}.bias"].to(device=device, dtype=dtype) for l in range(n_lin)]
+    return vs, gs, bs
+
+
+def _rel(a, b):
+    return (a.double().cpu() - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+@pytest.mark.parametrize("width,n,use_full,use_grad", [(256, 300, True, True), (512, 1000, True, True), (512, 17, True, False),
+                                                        (256, 4097, False, True)])
+def test_sdf_backward_vs_explicit_chain(width, n, use_full, use_grad):
+    dev = torch.device("cuda:0")
+    sd = synth.make_state_dict(width=width, seed=1, perturb=0.05, pe_noise=0.003, bias=0.6)
+    net = ops.PackedNet("sdf", width, 8).pack_state_dict(sd, "implicit_network", dev)
+    g = torch.Generator().manual_seed(n)
+    x = torch.rand(n, 3, generator=g) * 1.6 - 0.8
+    F = 256
+    g_full = torch.randn(n, F + 2, generator=g) * 1e-3 if use_full else None
+    g_grad = torch.randn(n, 3, generator=g) * 1e-2 if use_grad else None
+    vs, gs, bs = _sdf_lists(sd)
+    zf = torch.zeros(n, F + 2, dtype=torch.float64)
+    zg = torch.zeros(n, 3, dtype=torch.float64)
+    dx_ref, dv_ref, dg_ref, db_ref = S.sdf_value_grad_backward(x.double(), vs, gs, bs, (4,), 6,
+                                                               g_full.double() if use_full else zf,
+                                                               g_grad.double() if use_grad else zg)
+    full, grad, save = ops.sdf_forward_train(net, x.to(dev))
+    full0, grad0 = ops.sdf_value_grad(net, x.to(dev), ops.HEAD_FULL)
+    gate("forward_train_vs_forward_full", (full - full0).abs().max().item(), 5e-6)
+    gate("forward_train_vs_forward_grad", (grad - grad0).abs().max().item(), 5e-5)
+    dx, dw, db = ops.sdf_backward(net, x.to(dev), save, None if g_full is None else g_full.to(dev),
+                                  None if g_grad is None else g_grad.to(dev), need_dx=True)
+    gate("dx_rel_of_max", _rel(dx, dx_ref), G_DX)
+    v32, g32, _ = _sdf_lists(sd, dtype=torch.float32, device=dev)
+    dvs, dgs, dbs = ops.weight_grads(net, dw, db, v32, g32)
+    worst = 0.0
+    for l in range(9):
+        for name, got, ref in (("dv", dvs[l], dv_ref[l]), ("dg", dgs[l], dg_ref[l]), ("db", dbs[l], db_ref[l])):
+            if ref.abs().max().item() == 0.0:
+                assert got.abs().max().item() == 0.0, (l, name)
+                continue
+            e = _rel(got.reshape(ref.shape), ref)
+            worst = max(worst, e)
+            assert e < 5 * G_PARAM, f"layer {l} {name}: {e:.3e}"
+    gate("param_grad_rel_of_max", worst, G_PARAM)
+    # the saved activations can be swept more than once (the surface set gets two sweeps per step)
+    dx2, dw2, db2 = ops.sdf_backward(net, x.to(dev), save, None if g_full is None else g_full.to(dev),
+                                     None if g_grad is None else g_grad.to(dev), need_dx=True)
+    assert torch.allclose(dx, dx2, rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("width,n", [(256, 200), (512, 1000), (512, 65)])
+def test_render_backward_vs_explicit_chain(width, n):
+    dev = torch.device("cuda:0")
+    sd = synth.make_state_dict(width=width, seed=2, perturb=0.05, pe_noise=0.003, bias=0.6)
+    net = ops.PackedNet("render", width, 4, n_freqs=4).pack_state_dict(sd, "rendering_network", dev)
+    g = torch.Generator().manual_seed(n + 1)
+    pts = torch.rand(n, 3, generator=g) - 0.5
+    nrm = torch.randn(n, 3, generator=g)
+    view = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=1)
+    feats = torch.randn(n, 256, generator=g) * 0.5
+    g_rgb = torch.randn(n, 3, generator=g) * 1e-3
+    vs = [sd[f"rendering_network.lin{l}.weight_v"].double() for l in range(5)]
+    gs = [sd[f"rendering_network.lin{l}.weight_g"].double() for l in range(5)]
+    bs = [sd[f"rendering_network.lin{l}.bias"].double() for l in range(5)]
+    dp_ref, dn_ref, _, df_ref, dv_ref, dg_ref, db_ref = S.render_backward(pts.double(), nrm.double(), view.double(), feats.double(),
+                                                                         vs, gs, bs, 4, g_rgb.double())
+    rgb, save = ops.render_forward_train(net, pts.to(dev), view.to(dev), nrm.to(dev), feats.to(dev))
+    rgb0 = ops.render_forward(net, pts.to(dev), view.to(dev), nrm.to(dev), feats.to(dev))
+    gate("render_forward_train_vs_forward", (rgb - rgb0).abs().max().item(), 5e-6)
+    d_points, d_normals, d_feats, dw, db = ops.render_backward(net, save, rgb, g_rgb.to(dev))
+    gate("d_points_rel", _rel(d_points, dp_ref), G_DX)
+    gate("d_normals_rel", _rel(d_normals, dn_ref), G_DX)
+    gate("d_feats_rel", _rel(d_feats, df_ref), G_DX)
+    dvs, dgs, dbs = ops.weight_grads(net, dw, db, [v.float().to(dev) for v in vs], [x.float().to(dev) for x in gs])
+    worst = 0.0
+    for l in range(5):
+        for got, ref in ((dvs[l], dv_ref[l]), (dgs[l], dg_ref[l]), (dbs[l], db_ref[l])):
+            worst = max(worst, _rel(got.reshape(ref.shape), ref))
+    gate("param_grad_rel_of_max", worst, G_PARAM)
+
+
+def test_fused_adam_matches_torch_adam_with_clipping():
+    from mvsdf_b200.optim import B200Adam
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    shapes = [(512, 39), (512, 1), (512,), (473, 512), (3, 512), (3,)]
+    base = [torch.randn(*s, generator=g) for s in shapes]
+    ours = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    theirs = [torch.nn.Parameter(b.clone().to(dev)) for b in base]
+    opt_a = B200Adam(ours, lr=2e-4 * 8)
+    opt_b = torch.optim.Adam(theirs, lr=2e-4 * 8)
+    for step in range(4):
+        grads = [torch.randn(*s, generator=g).to(dev) * (3.0 if step % 2 else 0.01) for s in shapes]
+        for p, q, gr in zip(ours, theirs, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        total = torch.cat([gr.flatten() for gr in grads]).norm()
+        torch.nn.utils.clip_grad_norm_(theirs, 2.0)
+        opt_b.step()
+        opt_a.step(max_grad_norm=2.0)
+        assert abs(float(opt_a.grad_norm) - float(total)) < 1e-4 * float(total)
+        for p, q in zip(ours, theirs):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), step

@@ -136,8 +136,13 @@ def _subsample_parity(model, scene, dev, n_sub, seed, full_out=None):
     out = model({k: sub[k].to(dev) for k in IN_KEYS})
     losses = B200IDRLoss().hot_path_losses(out, {k: sub[k].to(dev) for k in GT_KEYS}, 0.5)
     if full_out is not None:       # the sub-sample run IS the full-size run restricted to these rays
-        for k in ("points", "rgb_values", "sdf_output", "network_object_mask"):
-            assert _same(full_out[k][idx.to(dev)], out[k]), f"{k}: sub-sample run differs from the full-image run"
+        for k in ("points", "rgb_values", "network_object_mask", "diff_surf_pts"):
+            want = full_out[k][idx.to(dev)] if k != "diff_surf_pts" else full_out["points"][idx.to(dev)][out["network_object_mask"]]
+            assert _same(want, out[k]), f"{k}: sub-sample run differs from the full-image run"
+        # sdf_output is the one launch with a host-known count: 4 096 points take the single-CTA scheduling of the tile
+        # core (mlp_kernel.cuh), 1.92 M the CTA-pair kernel, whose softplus is formulated differently -- same value to fp32
+        # rounding, not the same bits
+        gate("sdf_output_small_vs_pair_kernel", (full_out["sdf_output"][idx.to(dev)] - out["sdf_output"]).abs().max().item(), 2e-6)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     with torch.no_grad():
         ref = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), sub, None, False)
@@ -151,15 +156,15 @@ def _subsample_parity(model, scene, dev, n_sub, seed, full_out=None):
     d_ref = (ref["points"] - cam).norm(dim=1)[both]
     d_new = (out["points"].cpu() - cam).norm(dim=1)[both]
     rel = (d_new - d_ref).abs() / d_ref
-    gate("depth_rel_frac_above_1e-4", (rel > 1e-4).float().mean().item(), 0.01, f"(max {rel.max():.2e})")
+    gate("depth_rel_frac_above_1e-4", (rel > 1e-4).float().mean().item(), 0.002, f"(max {rel.max():.2e})")
     gate("depth_rel_median", rel.median().item(), 2e-5)
     rgb_err = (out["rgb_values"].cpu() - ref["rgb_values"]).abs().max(dim=1).values[both]
-    gate("rgb_abs_median", rgb_err.median().item(), 1e-4)
-    gate("rgb_abs_frac_above_1e-3", (rgb_err > 1e-3).float().mean().item(), 0.01, f"(max {rgb_err.max():.2e})")
+    gate("rgb_abs_median", rgb_err.median().item(), 5e-7)
+    gate("rgb_abs_frac_above_1e-5", (rgb_err > 1e-5).float().mean().item(), 0.002, f"(max {rgb_err.max():.2e})")
     if flips == 0:
-        gate("diff_surf_pts_abs_max", (out["diff_surf_pts"].cpu() - ref["diff_surf_pts"]).abs().max().item(), 5e-4)
-        gate("rgb_loss_rel", abs(float(losses["rgb_loss"]) - float(ref_l["rgb_loss"])) / abs(float(ref_l["rgb_loss"])), 1e-3)
-        gate("feat_loss_rel", abs(float(losses["feat_loss"]) - float(ref_l["feat_loss"])) / abs(float(ref_l["feat_loss"])), 2e-2)
+        gate("diff_surf_pts_abs_max", (out["diff_surf_pts"].cpu() - ref["diff_surf_pts"]).abs().max().item(), 3e-4)
+        gate("rgb_loss_rel", abs(float(losses["rgb_loss"]) - float(ref_l["rgb_loss"])) / abs(float(ref_l["rgb_loss"])), 2e-6)
+        gate("feat_loss_rel", abs(float(losses["feat_loss"]) - float(ref_l["feat_loss"])) / abs(float(ref_l["feat_loss"])), 1.5e-4)
     else:
         gate("rgb_loss_abs", abs(float(losses["rgb_loss"]) - float(ref_l["rgb_loss"])), 5e-3)
 

@@ -49,19 +49,20 @@ def _check_forward(out, g, scene, training):
 
 
 # gate limits (see _check_forward)
-G_FLIPS = 2
-G_DEPTH_FRAC = 0.01
-G_DEPTH_MAX = 1.0
-G_DEPTH_MEDIAN = 2e-5
-G_RGB_MAX = 1.0
-G_RGB_MEDIAN = 1e-4
-G_SDF_MAX = 1.0
-G_SURF_PTS = 5e-4
-G_RGB_LOSS_REL = 1e-3
-G_FEAT_LOSS_REL = 2e-2
-G_GRAD_THETA = 5e-3
-G_EIK_LOSS_REL = 1e-3
-G_SURF_LOSS_REL = 1e-4
+# measured on the B200 (profiles/r02/gate_report.json), worst case over the fixtures -> limit
+G_FLIPS = 1                 # 0 flips on every fixture
+G_DEPTH_FRAC = 0.002        # 0 rays above 1e-4
+G_DEPTH_MAX = 1.5e-4        # 5.1e-5
+G_DEPTH_MEDIAN = 2e-5       # 5.6e-6
+G_RGB_MAX = 1e-5            # 1.6e-6
+G_RGB_MEDIAN = 5e-7         # 1.2e-7
+G_SDF_MAX = 1e-4            # 3.6e-5
+G_SURF_PTS = 3e-4           # 1.0e-4
+G_RGB_LOSS_REL = 2e-6       # 1.1e-7
+G_FEAT_LOSS_REL = 1.5e-4    # 4.2e-5
+G_GRAD_THETA = 2e-3         # 6.6e-4
+G_EIK_LOSS_REL = 1.5e-4     # 4.1e-5
+G_SURF_LOSS_REL = 1.5e-5    # 4.2e-6
 
 
 @pytest.mark.parametrize("name", ["cfg1_eval_w256", "small_eval_w512", "cfg2_shape_eval_w512"])
@@ -82,7 +83,7 @@ def test_eval_forward_vs_reference_golden(golden, name):
         gate("rgb_loss_rel", rel_err(losses["rgb_loss"].cpu(), g["rgb_loss"]), G_RGB_LOSS_REL)
         gate("feat_loss_rel", rel_err(losses["feat_loss"].cpu(), g["feat_loss"]), G_FEAT_LOSS_REL)
     else:
-        assert abs(float(losses["rgb_loss"]) - float(g["rgb_loss"])) < 0.02
+        gate("rgb_loss_abs_with_flips", abs(float(losses["rgb_loss"]) - float(g["rgb_loss"])), 0.01)
 
 
 @pytest.mark.parametrize("name", ["cfg1_train_w256", "cfg3_shape_train_w512"])
@@ -138,10 +139,10 @@ def test_full_loss_dict_vs_reference_golden(golden):
     res = B200IDRLoss()(out, gt, tp, 2)
     assert set(res) == {"loss", "rgb_loss", "eikonal_loss", "depth_loss", "feat_loss", "surf_loss"}
     if int((out["network_object_mask"].cpu() != t(g["network_object_mask"])).sum()) == 0:
-        assert rel_err(res["depth_loss"].cpu(), g["depth_loss"]) < 2e-3
+        gate("depth_loss_rel", rel_err(res["depth_loss"].cpu(), g["depth_loss"]), 2e-4)
         want = (0.5 * float(g["rgb_loss"]) + conf.eikonal_weight * float(g["eikonal_loss"]) + conf.surf_weight * float(g["surf_loss"])
                 + conf.feat_weight(tp) * float(g["feat_loss"]) + float(g["depth_loss"]))
-        assert abs(float(res["loss"]) - want) < 2e-3 * abs(want)
+        gate("total_loss_rel", abs(float(res["loss"]) - want) / abs(want), 2e-4)
 
 
 def test_train_phase0_forward_vs_reference_golden(golden):
@@ -203,7 +204,7 @@ def test_tracer_vs_reference_golden(golden, name):
     with torch.no_grad():
         O.trace_rays(lambda x: O.sdf_mlp(x, sw)[:, 0], o_cam, scene["object_mask"].reshape(-1), o_dirs, training=training,
                      steps01=steps, counters=oc)
-    gate("e_trace_rel_diff", abs(e_trace - oc.total) / oc.total, 0.01, f"({e_trace} vs {oc.total})")
+    gate("e_trace_rel_diff", abs(e_trace - oc.total) / oc.total, 1e-3, f"({e_trace} vs {oc.total})")
     if model.prefilter_tau > 0:
         assert int(cnt[_lib.CTR_SCREENED]) + int(cnt[_lib.CTR_REFINED]) < oc.sampler + oc.min_sdf or oc.sampler + oc.min_sdf == 0
 

@@ -108,7 +108,7 @@ def _stress_state_dict(name):
     return synth.make_state_dict(**STRESS_PRESETS[name]), STRESS_PRESETS[name]["width"]
 
 
-@pytest.mark.parametrize("name", ["w256_p10", "w256_pe20", "w512_p10", "trained_like_w256"])
+@pytest.mark.parametrize("name", ["w256_p10", "w256_pe8", "w512_p10", "trained_like_w256"])
 def test_prefilter_with_guard_stays_bit_identical_on_stress_weights(name):
     """The screening error depends on the weights.  Whatever it is for these networks, forward() (prefilter + unbiased
     guard + exact fallback + tau widening) must return exactly the prefilter-off outputs, on the first call and after the
@@ -125,7 +125,7 @@ def test_prefilter_with_guard_stays_bit_identical_on_stress_weights(name):
     net = model.implicit_network.packed()
     x = (torch.rand(200000, 3, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(dev)
     err = (ops.sdf_forward(net, x, ops.HEAD_SDF_SCREEN) - ops.sdf_forward(net, x, ops.HEAD_SDF_ONLY)).abs().max().item()
-    gate("screening_abs_err_max", err, 2.5e-2, f"({name})")
+    gate("screening_abs_err_max", err, 4e-3, f"({name})")
     tau0 = model.prefilter_tau
     model.prefilter_tau = 0.0
     ref = {k: v.clone() if isinstance(v, torch.Tensor) else v for k, v in model(inp).items()}
