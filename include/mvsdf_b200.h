@@ -48,6 +48,7 @@ const char* mvsdf_last_error(void);
  * entries).  mvsdf_profile_collect synchronises on the recorded events. */
 #define MVSDF_PROFILE_KINDS 8
 long long mvsdf_launch_count(void);
+void mvsdf_launch_count_add(long long n);   /* a caller that replays a captured CUDA graph of library launches reports them */
 void mvsdf_profile_enable(int on);
 int mvsdf_profile_collect(float* ms_by_kind_host, int* launches_by_kind_host);
 

@@ -28,6 +28,8 @@ def _declare(lib):
     lib.mvsdf_abi_version.restype = c_int
     lib.mvsdf_last_error.restype = c_char_p
     lib.mvsdf_launch_count.restype = ctypes.c_longlong
+    lib.mvsdf_launch_count_add.restype = None
+    lib.mvsdf_launch_count_add.argtypes = [ctypes.c_longlong]
     lib.mvsdf_profile_enable.restype = None
     lib.mvsdf_profile_enable.argtypes = [c_int]
     lib.mvsdf_profile_collect.restype = c_int

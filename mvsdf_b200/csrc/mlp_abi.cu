@@ -318,6 +318,7 @@ int mvsdf_abi_version(void) { return 1; }
 /* debug only (not in the public header): device buffer of >= 1 MiB that receives a clock64 timeline of CTA pair 0 */
 void mvsdf_debug_set_trace(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
 long long mvsdf_launch_count(void) { return g_launches; }
+void mvsdf_launch_count_add(long long n) { g_launches += n; }
 void mvsdf_profile_enable(int on) {
   g_prof_on = on != 0;
   g_prof_used = 0;

@@ -283,6 +283,13 @@ class B200IDRNetwork(nn.Module):
         self.prefilter_fallbacks = 0       # forwards repeated exactly because the screening guard tripped
         self._ws: Dict[str, torch.Tensor] = {}
         self.last_trace_counters: Optional[torch.Tensor] = None
+        # CUDA graphs: the launch sequence of a forward is static and sync-free (device-side counts everywhere), so for
+        # small ray counts -- where ~170-330 launches per step leave the GPU waiting for the host -- the whole sequence is
+        # captured once per (shape, mode, tracer settings) and replayed
+        self.use_graphs = os.environ.get("MVSDF_GRAPHS", "1") != "0"
+        self.graph_max_rays = 1 << 18
+        self._graphs: Dict[tuple, dict] = {}
+        self.graph_replays = 0
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, name: str, nbytes: int, device) -> torch.Tensor:
@@ -290,6 +297,13 @@ class B200IDRNetwork(nn.Module):
         if t is None or t.numel() < nbytes or t.device != device:
             t = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._ws[name] = t
+        return t
+
+    def _linspace(self, dev):
+        t = self._ws.get("linspace")
+        if t is None or t.device != dev:
+            t = torch.linspace(0, 1, steps=self.tracer_conf["n_steps"]).to(dev)
+            self._ws["linspace"] = t
         return t
 
     def _tracer_params(self, L):
@@ -325,7 +339,7 @@ class B200IDRNetwork(nn.Module):
         net_mask = torch.empty(R, dtype=torch.uint8, device=dev)
         points = torch.empty(R, 3, **f)
         counters = torch.empty(256, dtype=torch.int32, device=dev)
-        lin = torch.linspace(0, 1, steps=self.tracer_conf["n_steps"]).to(dev)        # ray_tracing.py:206
+        lin = self._linspace(dev)                                                     # ray_tracing.py:206
         steps = None
         if training and not self.skip_min_sdf:
             # same draw as ray_tracing.py:287: CPU default generator, then moved to the device
@@ -521,7 +535,6 @@ class B200IDRNetwork(nn.Module):
         }
 
     def _forward_native(self, input, train_progress=None, steps01=None, eik_points=None, dsurf_rand=None):
-        L = _lib.lib()
         conf = self.schedule
         uv = ops._f32(input["uv"])
         pose = ops._f32(input["pose"])
@@ -533,20 +546,74 @@ class B200IDRNetwork(nn.Module):
             pose = _quaternion_pose(pose)
         B, N, _ = uv.shape
         R = B * N
-        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
-        sdf_net = self.implicit_network.packed()
-        rend_net = self.rendering_network.packed()
         obj_u8 = object_mask.to(torch.uint8).contiguous()
         training = self.training
         use_dsurf = False
+        steps_dev = extra_pts = None
+        n_eik = R // 2
         if training:
             assert train_progress is not None
             use_dsurf = self._phase0(train_progress)
-        ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics, obj_u8, training, steps01)
-        network_object_mask = net_u8.bool()
-        surface_u8 = (net_u8 & obj_u8) if training else net_u8
+            if not self.skip_min_sdf:
+                # same draw as ray_tracing.py:287: CPU default generator, then moved to the device
+                steps_dev = (steps01 if steps01 is not None else torch.empty(self.tracer_conf["n_steps"]).uniform_(0.0, 1.0))
+                steps_dev = steps_dev.to(device=dev, dtype=torch.float32).contiguous()
+            if eik_points is None:
+                r = self.object_bounding_sphere      # :216-221, CPU generator then .cuda()
+                eik_points = torch.empty(n_eik, 3).uniform_(-r, r)
+            extra_pts = eik_points.to(device=dev, dtype=torch.float32).contiguous()
+            if use_dsurf:                                # :226-251: on-surface and jittered depth samples join the set
+                ds_on, ds_jit = self.depth_surface_samples(input, n_eik, dsurf_rand)
+                extra_pts = torch.cat([extra_pts, ds_on, ds_jit], dim=0).contiguous()
+        args = (uv, pose, intrinsics, obj_u8, steps_dev, extra_pts)
+        if self.use_graphs and R <= self.graph_max_rays:
+            raw = self._replay_native(training, *args)
+        else:
+            raw = self._enqueue_native(training, *args)
+        # the single host sync: diff_surf_pts has a data-dependent shape (+ guard and range monitors in the same read)
+        M, failed = self._host_checks(raw["sdf_net"], raw["rend_net"], raw["hit_offsets"][B])
+        if failed:
+            return self._redo_exact(self._forward_native, input, train_progress, steps01, eik_points, dsurf_rand)
+        surf_pts, normals, surf_head, hit_index = raw["surf_pts"], raw["normals"], raw["surf_head"], raw["hit_index"]
+        diff_surf_pts = surf_pts[:M]
+        output = {
+            "points": raw["points"],
+            "diff_surf_pts": diff_surf_pts,
+            "rgb_values": raw["rgb_values"],
+            "sdf_output": raw["sdf_out"].unsqueeze(1),
+            "network_object_mask": raw["net_u8"].bool(),
+            "object_mask": object_mask,
+            "object_mask_true": object_mask_true,
+            "grad_theta": None,
+            # extras (not in the reference dict) consumed by B200IDRLoss to skip recomputation
+            "hit_offsets": raw["hit_offsets"],
+            "surface_normals": normals[:M],
+            "ray_dirs": raw["ray_dirs"],
+            "dists": raw["dists"],
+        }
+        if training:
+            extra, g_extra = raw["extra"], raw["g_extra"]
+            f_s = surf_head[:M, 0:1]
+            eik_pts = torch.cat([diff_surf_pts, extra_pts], dim=0)
+            output["eikonal_output"] = torch.cat([f_s, extra[:, :1]], dim=0).view(1, -1)
+            output["eikonal_points_hom"] = torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1)
+            keep = object_mask_true[hit_index[:M].long()]
+            output["surf_indicator_output"] = torch.cat([surf_head[:M, 1][keep], extra[:n_eik, 1]], dim=0)
+            output["grad_theta"] = torch.cat([normals[:M], g_extra], dim=0)
+        return output
 
+    def _enqueue_native(self, training, uv, pose, intrinsics, obj_u8, steps_dev, extra_pts):
+        """Every launch of a no-grad forward, enqueue only: weight packing, tracer, shading and (training) the value +
+        gradient pass over the eikonal samples.  No host read, no data-dependent shape -- capturable in a CUDA graph."""
+        L = _lib.lib()
+        dev = uv.device
+        B, N, _ = uv.shape
+        R = B * N
+        stream = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        sdf_net = self.implicit_network.packed()
+        rend_net = self.rendering_network.packed()
+        ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics, obj_u8, training, steps_dev)
+        surface_u8 = (net_u8 & obj_u8) if training else net_u8
         f = dict(dtype=torch.float32, device=dev)
         sdf_out = torch.empty(R, **f)
         rgb_values = torch.empty(R, 3, **f)
@@ -562,42 +629,53 @@ class B200IDRNetwork(nn.Module):
                                       _lib.ptr(ws), _lib.ptr(sdf_out), _lib.ptr(rgb_values), _lib.ptr(surf_pts),
                                       _lib.ptr(normals), _lib.ptr(surf_head), _lib.ptr(hit_index), _lib.ptr(hit_offsets),
                                       stream))
-        # the single host sync: diff_surf_pts has a data-dependent shape (+ guard and range monitors in the same read)
-        M, failed = self._host_checks(sdf_net, rend_net, hit_offsets[B])
-        if failed:
-            return self._redo_exact(self._forward_native, input, train_progress, steps01, eik_points, dsurf_rand)
-        diff_surf_pts = surf_pts[:M]
-        output = {
-            "points": points,
-            "diff_surf_pts": diff_surf_pts,
-            "rgb_values": rgb_values,
-            "sdf_output": sdf_out.unsqueeze(1),
-            "network_object_mask": network_object_mask,
-            "object_mask": object_mask,
-            "object_mask_true": object_mask_true,
-            "grad_theta": None,
-            # extras (not in the reference dict) consumed by B200IDRLoss to skip recomputation
-            "hit_offsets": hit_offsets,
-            "surface_normals": normals[:M],
-            "ray_dirs": ray_dirs,
-            "dists": dists,
-        }
+        raw = dict(sdf_net=sdf_net, rend_net=rend_net, ray_dirs=ray_dirs, cam_loc=cam_loc, dists=dists, net_u8=net_u8, points=points,
+                   sdf_out=sdf_out, rgb_values=rgb_values, surf_pts=surf_pts, normals=normals, surf_head=surf_head,
+                   hit_index=hit_index, hit_offsets=hit_offsets, counters=self.last_trace_counters)
         if training:
-            n_eik = R // 2
-            if eik_points is None:
-                r = self.object_bounding_sphere      # :216-221, CPU generator then .cuda()
-                eik_points = torch.empty(n_eik, 3).uniform_(-r, r)
-            eik_points = eik_points.to(device=dev, dtype=torch.float32).contiguous()
-            extra_pts = eik_points
-            if use_dsurf:                                # :226-251: on-surface and jittered depth samples join the set
-                ds_on, ds_jit = self.depth_surface_samples(input, n_eik, dsurf_rand)
-                extra_pts = torch.cat([eik_points, ds_on, ds_jit], dim=0).contiguous()
-            extra, g_extra = ops.sdf_value_grad(sdf_net, extra_pts, ops.HEAD_FULL)
-            f_s = surf_head[:M, 0:1]
-            eik_pts = torch.cat([diff_surf_pts, extra_pts], dim=0)
-            output["eikonal_output"] = torch.cat([f_s, extra[:, :1]], dim=0).view(1, -1)
-            output["eikonal_points_hom"] = torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1)
-            keep = object_mask_true[hit_index[:M].long()]
-            output["surf_indicator_output"] = torch.cat([surf_head[:M, 1][keep], extra[:n_eik, 1]], dim=0)
-            output["grad_theta"] = torch.cat([normals[:M], g_extra], dim=0)
-        return output
+            raw["extra"], raw["g_extra"] = ops.sdf_value_grad(sdf_net, extra_pts, ops.HEAD_FULL)
+        return raw
+
+    _GRAPH_OUT = ("ray_dirs", "cam_loc", "dists", "net_u8", "points", "sdf_out", "rgb_values", "surf_pts", "normals", "surf_head",
+                  "hit_index", "hit_offsets", "extra", "g_extra")
+
+    def _replay_native(self, training, uv, pose, intrinsics, obj_u8, steps_dev, extra_pts):
+        """_enqueue_native through a CUDA graph captured once per (shapes, mode, tracer settings, parameter storage)."""
+        L = _lib.lib()
+        dev = uv.device
+        live = [uv, pose, intrinsics, obj_u8, steps_dev, extra_pts]
+        pkey = tuple(p.data_ptr() for p in self.parameters())
+        tkey = tuple(sorted(self.tracer_conf.items())) + (os.environ.get("IDR_USE_ENV", "0"), os.environ.get("IDR_RENDER", "0"))
+        key = (training, bool(self.skip_min_sdf), float(self.prefilter_tau), str(dev), pkey, tkey,
+               tuple(None if t is None else (tuple(t.shape), t.dtype) for t in live))
+        g = self._graphs.get(key)
+        if g is None:
+            static = [None if t is None else t.clone() for t in live]
+            # eager warm-up on a side stream: sizes the workspaces, sets the kernels' attributes, allocates the blobs
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._enqueue_native(training, *static)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.mvsdf_launch_count()
+            with torch.cuda.graph(graph):
+                raw = self._enqueue_native(training, *static)
+            g = dict(graph=graph, static=static, raw=raw, launches=L.mvsdf_launch_count() - n0)
+            if len(self._graphs) >= 8:                       # bounded cache (e.g. tau widening creates new keys)
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = g
+        for dst, src in zip(g["static"], live):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        g["graph"].replay()
+        L.mvsdf_launch_count_add(g["launches"])              # replayed kernels count as launches of the library
+        self.graph_replays += 1
+        raw = dict(g["raw"])
+        self.last_trace_counters = raw["counters"]
+        # hand out copies: the graph's output buffers are overwritten by the next replay
+        for k in self._GRAPH_OUT:
+            if k in raw and raw[k] is not None:
+                raw[k] = raw[k].clone()
+        return raw
