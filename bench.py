@@ -41,6 +41,12 @@ WORKLOADS = {
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
     "cfg3": dict(H=1200, W=1600, width=512, n_src=8, n_images=2, n_rays=4096, training=True,
                  weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
+    # the reference's training step (confs/mvsdf_dtu.conf:4 num_pixels = 4096, training/exp_runner.py:12 batch_size = 8,
+    # scene_dataset.py:104 num_src = 2): forward + the five losses + backward + Adam, train_progress = 0.5
+    "train32k": dict(H=1200, W=1600, width=512, n_src=2, n_images=8, n_rays=4096, training=True, train_step=True,
+                     weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
+    "train8k": dict(H=1200, W=1600, width=512, n_src=2, n_images=2, n_rays=4096, training=True, train_step=True,
+                    weights=dict(width=512, seed=0, perturb=0.05, pe_noise=0.003, bias=0.75)),
     "cfg1": dict(H=32, W=32, width=256, n_src=1, n_images=1, n_rays=None, training=False,
                  weights=dict(width=256, seed=1, perturb=0.05, pe_noise=0.003, bias=0.6)),
     # BASELINE.json configs[3]: ONE 1.2 M-ray image sharded across the ranks as contiguous ray ranges (strong scaling):
@@ -213,6 +219,20 @@ def run_ours(args):
     n_kind = (ctypes.c_int * 8)()
     _lib.check(L.mvsdf_profile_collect(ms_kind, n_kind))
     L.mvsdf_profile_enable(0)
+    graphs_used = getattr(model, "graph_replays", 0) > 0
+    if graphs_used and sum(n_kind) == 0:
+        # small workloads replay a captured CUDA graph: no host code runs per launch, so the per-launch events of the
+        # roofline leg are taken in a separate pass with the graph off (same kernels, same inputs; `value` stays the graph run)
+        model.use_graphs = False
+        step(resident)
+        barrier()
+        L.mvsdf_profile_enable(1)
+        for _ in range(args.steps):
+            step(resident)
+        barrier()
+        _lib.check(L.mvsdf_profile_collect(ms_kind, n_kind))
+        L.mvsdf_profile_enable(0)
+        model.use_graphs = True
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -311,6 +331,7 @@ def run_ours(args):
                        "feature_store": f"{scene_bytes} bytes of scene feature maps resident channels-last (uploaded once, not per step)",
                        "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
                        "skip_min_sdf": bool(args.skip_min_sdf),
+                       "cuda_graph": bool(graphs_used),
                        "prefilter": {"tau": model.prefilter_tau, "screened_evals_per_ray": screened / R, "refined_evals_per_ray": refined / R,
                                      "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
                                      "note": "100-sample stages: screening pass (1 fp16 product, 5 chunks of 10-30 samples, stops behind "
@@ -346,6 +367,183 @@ def run_ours(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+TRAIN_GT_KEYS = GT_KEYS + ["depths", "depth_cams"]
+
+
+def run_train(args):
+    """`--workload train32k`: one optimisation step of the reference's training loop (idr_train.py:268-300) through the
+    drop-in modules -- B200IDRNetwork.forward (training mode, autograd on), B200IDRLoss.forward (rgb + eikonal + surface
+    indicator + feature consistency + depth carving), loss.backward() (native reverse sweep + dW GEMM, mlp_bwd_kernel.cuh),
+    B200Adam.step with the reference's gradient-norm cap -- on 8 images x 4096 rays, train_progress = 0.5."""
+    import ctypes
+    from mvsdf_b200 import _lib, conf as schedule
+    from mvsdf_b200.loss import B200IDRLoss
+    from mvsdf_b200.network import B200IDRNetwork, default_conf
+    from mvsdf_b200.optim import B200Adam
+
+    assert args.gpus == 1, "the training-step bench is a single-GPU line"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    cfg = WORKLOADS[args.workload]
+    scene, sd = make_inputs(cfg, 0, 1, shard=False)
+    B, N = scene["uv"].shape[:2]
+    R = B * N
+    tp = 0.5
+    model = B200IDRNetwork(default_conf(cfg["width"])).to(dev)
+    model.load_state_dict(sd)
+    model.train()
+    model.skip_min_sdf = bool(args.skip_min_sdf)
+    loss_mod = B200IDRLoss()
+    opt = B200Adam(model.parameters(), lr=2.0e-4 * B)            # idr_train.py:110-113: lr scaled by the batch size
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1234)
+    steps01 = torch.rand(100, generator=g)
+    eik = torch.rand(R // 2, 3, generator=g) * 2 - 1
+    host = pin({k: scene[k] for k in IN_KEYS + TRAIN_GT_KEYS})
+    resident = {k: host[k].to(dev) for k in IN_KEYS + TRAIN_GT_KEYS}
+    cap = schedule.grad_cap(tp) if (schedule.phase[0] <= tp and schedule.enable_grad_cap) else None
+
+    def step(inputs):
+        out = model({k: inputs[k] for k in IN_KEYS + ["depths", "depth_cams", "size", "center"]}, tp, steps01=steps01, eik_points=eik)
+        ls = loss_mod(out, {k: inputs[k] for k in TRAIN_GT_KEYS}, tp, B)
+        opt.zero_grad(set_to_none=True)
+        ls["loss"].sum().backward()
+        opt.step(max_grad_norm=cap)
+        return out, ls
+
+    for _ in range(args.warmup):
+        step(resident)
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(0)
+    clocks.start()
+    launches0 = L.mvsdf_launch_count()
+    L.mvsdf_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out, ls = step(resident)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop()
+    launches = L.mvsdf_launch_count() - launches0
+    ms_kind = (ctypes.c_float * 8)()
+    n_kind = (ctypes.c_int * 8)()
+    _lib.check(L.mvsdf_profile_collect(ms_kind, n_kind))
+    L.mvsdf_profile_enable(0)
+    n_hit = int(out["hit_offsets"][-1].item())
+    cnt = model.last_trace_counters.cpu()
+    evals = int(cnt[:_lib.CTR_SCREENED].sum().item())
+
+    # e2e: the step's inputs come from pinned host memory, the loss scalar goes back
+    step_keys = [k for k in IN_KEYS + TRAIN_GT_KEYS if k not in SCENE_KEYS]
+
+    def h2d_step():
+        inputs = {k: host[k].to(dev, non_blocking=True) for k in step_keys}
+        for k in SCENE_KEYS:
+            inputs[k] = host[k]
+        _, l2 = step(inputs)
+        return l2["loss"].detach().reshape(-1)[:1].cpu()
+
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in step_keys)
+    h2d_step()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(args.steps):
+        lv = h2d_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    width = cfg["width"]
+    fl = FLOP[width]
+    # backward of the two MLPs, algorithmic: per swept SDF point 4 columns x (dX + dW) = 8 full-head passes; the surface set
+    # is swept twice (x_diff and x_s nodes), the eikonal set once; rendering net: 2 passes per hit
+    swept = 2 * n_hit + R // 2
+    bwd_flops = swept * 8 * fl["full"] + n_hit * 2 * fl["render"]
+    ms_bwd = (ms_kind[5] + ms_kind[6]) / args.steps
+    peaks = load_peaks()
+    achieved = bwd_flops / (ms_bwd * 1e-3) / 1e12 if ms_bwd > 0 else None
+    base = None
+    if not args.no_cpu_baseline:
+        try:
+            base = torch_cuda_port_train_sample(cfg, scene, sd, dev, tp, steps01, eik)
+        except Exception as e:
+            base = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    line = {
+        "metric": "rays/sec (training step: forward + 5 losses + backward + Adam) at 8 x 4096 rays, DTU-shaped",
+        "value": R / (ms_per_step * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32-equivalent (fp16 hi/lo split operands, fp32 tensor-core accumulate), fp32 Adam", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {B} images x {N} rays, {cfg['n_src']} src views, 8x{width} SDF MLP + 4x{width} render "
+                               f"MLP, train_progress {tp}: IDRNetwork.forward(train) + IDRLoss.forward (rgb, eikonal, surf, feat, depth) "
+                               f"+ backward + Adam(lr 2e-4 x {B}, grad cap {cap})",
+                   "rays": R, "hit_fraction": n_hit / R, "tracer_evals_per_ray": evals / R, "skip_min_sdf": bool(args.skip_min_sdf),
+                   "swept_points": swept, "l2_policy": "inputs + saved activations (>= 2 GB per step) larger than L2"},
+        "clocks": clk,
+        "e2e": {"value": R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4 + 4 * 7},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "mlp_bwd_sweep_kernel + mlp_bwd_dw_kernel (reverse sweep and dW GEMM of both MLPs)",
+                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                     "kernel_ms_per_step": ms_bwd, "sweep_ms_per_step": ms_kind[5] / args.steps, "dw_ms_per_step": ms_kind[6] / args.steps,
+                     "kernel_share_of_step": ms_bwd / ms_per_step,
+                     "note": "algorithmic FLOPs = 2*MAC x 8 full-head passes per swept point (4 value/tangent columns x (dX, dW)) + 2 "
+                             "render passes per hit; every MAC issues 3 fp16 UMMAs (hi*hi + lo*hi + hi*lo)"},
+        "mlp_ms_per_step_by_kind": {"sdf_only": ms_kind[0] / args.steps, "sdf_screen": ms_kind[4] / args.steps,
+                                    "value_grad": ms_kind[2] / args.steps, "render": ms_kind[3] / args.steps,
+                                    "bwd_sweep": ms_kind[5] / args.steps, "bwd_dw": ms_kind[6] / args.steps},
+        "losses": {k: float(v.detach().reshape(-1)[0]) for k, v in ls.items()},
+        "grad_norm": float(opt.grad_norm),
+    }
+    if base:
+        line["cpu_baseline"] = {"value": base.get("value"), "unit": "rays/s", "cores": 0, "kind": "port",
+                                "sample": base.get("sample", base.get("unavailable")), "torch_cuda_port_train": base}
+    emit(line)
+
+
+def torch_cuda_port_train_sample(cfg, scene, sd, dev, tp, steps01, eik):
+    """The reference's training step as eager PyTorch-CUDA ops: the oracle port (unchanged) with its tensors on cuda:0,
+    autograd backward (create_graph=True second-order terms), clip_grad_norm_, torch.optim.Adam -- with and without
+    minimal_sdf_points."""
+    from oracle import mvsdf_oracle as O
+    to = lambda d: {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    sc = to(scene)
+    B, N = scene["uv"].shape[:2]
+    R = B * N
+    res = {}
+    for skip in (False, True):
+        params = {k: v.clone().to(dev).requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.Adam(list(params.values()), lr=2.0e-4 * B)
+
+        def one():
+            out = O.idr_forward(O.sdf_weights(params), O.render_weights(params), sc, tp, True, steps01=steps01.to(dev),
+                                eik_points=eik.to(dev), skip_min_sdf=skip)
+            rl = O.hot_path_losses(out, sc, tp)
+            total = (0.5 * rl["rgb_loss"] + 0.1 * rl["eikonal_loss"] + 0.01 * rl["surf_loss"] + O.feat_weight(tp) * rl["feat_loss"].sum()
+                     + rl["depth_loss"])
+            opt.zero_grad(set_to_none=True)
+            total.backward()
+            torch.nn.utils.clip_grad_norm_(list(params.values()), 0.5)
+            opt.step()
+            return float(total)
+
+        one()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n_it = 2
+        for _ in range(n_it):
+            one()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / n_it
+        res["skip_min_sdf" if skip else "with_min_sdf"] = {"rays_per_s": R / dt, "ms_per_step": dt * 1e3}
+    return {"value": res["with_min_sdf"]["rays_per_s"], "unit": "rays/s", "device": torch.cuda.get_device_name(dev), **res,
+            "sample": f"{R} rays ({B} x {N}), full training step (forward + 5 losses + autograd backward + clip + Adam), oracle port on "
+                      "cuda:0 (eager PyTorch fp32, TF32 off), 2 timed steps after 1 warm-up"}
 
 
 def cpu_reference_sample(cfg, scene, sd, budget_s=20.0, threads=None):
@@ -486,6 +684,8 @@ def main():
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif WORKLOADS[args.workload].get("train_step"):
+        run_train(args)
     else:
         run_ours(args)
 

@@ -44,8 +44,8 @@ int mvsdf_abi_version(void);
 const char* mvsdf_last_error(void);
 /* Instrumentation (no reference counterpart): cumulative number of CUDA kernels this library has launched, and
  * optional CUDA-event timing of the MLP tile launches on their own stream (kinds: 0 SDF-only head, 1 full head,
- * 2 value+gradient, 3 rendering net, 4 SDF-only head at screening precision; both arrays hold MVSDF_PROFILE_KINDS
- * entries).  mvsdf_profile_collect synchronises on the recorded events. */
+ * 2 value+gradient, 3 rendering net, 4 SDF-only head at screening precision, 5 backward sweep, 6 dW GEMM of the backward;
+ * both arrays hold MVSDF_PROFILE_KINDS entries).  mvsdf_profile_collect synchronises on the recorded events. */
 #define MVSDF_PROFILE_KINDS 8
 long long mvsdf_launch_count(void);
 void mvsdf_launch_count_add(long long n);   /* a caller that replays a captured CUDA graph of library launches reports them */
@@ -218,6 +218,22 @@ int mvsdf_depth_loss_partials(const float* eik_points, int point_stride, const f
 int mvsdf_rgb_l1_partials(const float* rgb_values, const float* rgb_gt, const uint8_t* mask, int64_t n_rays,
                           double* partials, void* stream);
 int mvsdf_rgb_l1_finalize(const double* partials, float* out_loss, void* stream);
+
+/* ---- FeatExt (code/utils/my_utils.py:693-708; UNet :595-690, BasicBlock :531-576), eval mode: the CNN whose finest output
+ * (32 channels at half resolution) are the feature maps of get_feat_loss_corr; run once per scene over all images
+ * (datasets/scene_dataset.py:138-149).  27 convolutions in the order documented in csrc/featext.cu (kFe[]): stem, encoder
+ * blocks, decoder, heads.  *_host = HOST arrays (27 entries) of device pointers: conv weights in PyTorch layout
+ * ([out,in,k,k]; ConvTranspose2d [in,out,k,k]) and, where a BatchNorm follows, its weight / bias / running_mean /
+ * running_var (NULL entries otherwise).  mvsdf_featext_pack folds BatchNorm and writes [tap][in][out] slabs + bias.
+ * mvsdf_featext_forward: images_nchw [n,3,H,W] (H, W multiples of 8) -> channels-last maps: out_half_nhwc [n,H/2,W/2,32]
+ * (= feat_ext(x)[2], written in the feature store's layout) and optionally the 1/4 and 1/8 maps (= [1], [0]). */
+int mvsdf_featext_num_convs(void);
+size_t mvsdf_featext_packed_floats(void);
+int mvsdf_featext_pack(const float* const* conv_weight_host, const float* const* bn_weight_host, const float* const* bn_bias_host,
+                       const float* const* bn_mean_host, const float* const* bn_var_host, float bn_eps, float* packed, void* stream);
+size_t mvsdf_featext_workspace_bytes(int n_images, int height, int width);
+int mvsdf_featext_forward(const float* packed, const float* images_nchw, int n_images, int height, int width, size_t workspace_bytes,
+                          void* workspace, float* out_eighth_nhwc, float* out_quarter_nhwc, float* out_half_nhwc, void* stream);
 
 /* ---- the training step: backward through the two MLPs + optimiser --------------------------
  * What eager autograd does in the reference: loss.backward() (code/training/idr_train.py:287) through

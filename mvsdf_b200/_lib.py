@@ -76,6 +76,15 @@ def _declare(lib):
     lib.mvsdf_adam_step.restype = c_int
     lib.mvsdf_adam_step.argtypes = [c_int, POINTER(P), POINTER(P), POINTER(P), POINTER(P), POINTER(c_int64), c_float, c_float, c_float,
                                     c_float, c_int, c_float, P, P, P]
+    # ---- FeatExt (csrc/featext.cu)
+    lib.mvsdf_featext_num_convs.restype = c_int
+    lib.mvsdf_featext_packed_floats.restype = c_size_t
+    lib.mvsdf_featext_pack.restype = c_int
+    lib.mvsdf_featext_pack.argtypes = [POINTER(P), POINTER(P), POINTER(P), POINTER(P), POINTER(P), c_float, P, P]
+    lib.mvsdf_featext_workspace_bytes.restype = c_size_t
+    lib.mvsdf_featext_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.mvsdf_featext_forward.restype = c_int
+    lib.mvsdf_featext_forward.argtypes = [P, P, c_int, c_int, c_int, c_size_t, P, P, P, P, P]
     class TracerParams(ctypes.Structure):
         _fields_ = [("object_bounding_sphere", c_float), ("sdf_threshold", c_float), ("line_search_step", c_float),
                     ("dist_clip", c_float), ("line_step_iters", c_int), ("sphere_tracing_iters", c_int),

@@ -69,7 +69,7 @@ class SdfEval(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         net = ctx.net
         n = x.shape[0]
-        needs = ctx.needs_input_grad[3:]
+        needs = ctx.needs_input_grad[2:]           # [x, v0, g0, b0, ...]
         if n == 0 or (g_full is None and g_grad is None):
             zeros = [torch.zeros_like(p) if nd else None for p, nd in zip(params, needs[1:])]
             return (None, None, torch.zeros_like(x) if needs[0] else None, *zeros)

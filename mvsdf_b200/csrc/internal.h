@@ -19,6 +19,9 @@ int fail(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int sm_count();
 void note_launch();   // counts kernel launches made by the library (mvsdf_launch_count)
+// optional CUDA-event timing of a launch (mvsdf_profile_*); kinds 5 = backward sweep, 6 = dW GEMM
+void* prof_begin_ext(int kind, cudaStream_t st);
+void prof_end_ext(void* handle, cudaStream_t st);
 
 // MLP tile launches (mlp_abi.cu)
 int mlp_sdf(const mvsdf_net* net, const void* packed, const float* x, int64_t n, const int32_t* n_dev, int head,

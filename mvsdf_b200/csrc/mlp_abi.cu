@@ -52,6 +52,8 @@ struct ProfEvent { cudaEvent_t e0, e1; int kind; };
 static bool g_prof_on = false;
 static std::vector<ProfEvent> g_prof_pool;
 static size_t g_prof_used = 0;
+void* prof_begin_ext(int kind, cudaStream_t st);
+void prof_end_ext(void* p, cudaStream_t st);
 static ProfEvent* prof_begin(int kind, cudaStream_t st) {
   if (!g_prof_on) return nullptr;
   if (g_prof_used == g_prof_pool.size()) {
@@ -66,6 +68,14 @@ static ProfEvent* prof_begin(int kind, cudaStream_t st) {
 }
 static void prof_end(ProfEvent* p, cudaStream_t st) {
   if (p) cudaEventRecord(p->e1, st);
+}
+// for the other translation units (train_abi.cu): the pool may grow between begin and end, so hand out the INDEX
+void* prof_begin_ext(int kind, cudaStream_t st) {
+  ProfEvent* p = prof_begin(kind, st);
+  return p ? reinterpret_cast<void*>((p - g_prof_pool.data()) + 1) : nullptr;
+}
+void prof_end_ext(void* h, cudaStream_t st) {
+  if (h) prof_end(&g_prof_pool[reinterpret_cast<size_t>(h) - 1], st);
 }
 
 static void finalize_plan(NetPlan& p) {

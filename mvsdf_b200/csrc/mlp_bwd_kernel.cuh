@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
                 }
                 if (MODE == 1 && have_h) {
                   const float bsum = o[0] + o[4] + o[8] + o[12];
-                  if (f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum);
+                  if (f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum * invS);
                 }
               } else {
                 float bsum = 0.0f;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
                   o[j] = h > 0.0f ? d[j] : 0.0f;                 // ReLU'
                   bsum += o[j];
                 }
-                if (have_h && f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum);
+                if (have_h && f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum * invS);
               }
               if (!have_h) {
 #pragma unroll

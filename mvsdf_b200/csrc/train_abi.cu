@@ -380,7 +380,9 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
     return rc;
   const int grid = (int)std::min<long long>(n_tiles, sms);
   note_launch();
+  void* pe = prof_begin_ext(5, st);
   kern<<<grid, kMlpThreads, smem, st>>>(a);
+  prof_end_ext(pe, st);
   if ((rc = check_cuda(cudaGetLastError(), "launch mlp_bwd_sweep_kernel"))) return rc;
 
   // dW over the points
@@ -412,7 +414,9 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
                        "cudaFuncSetAttribute(mlp_bwd_dw_kernel)")))
     return rc;
   note_launch();
+  pe = prof_begin_ext(6, st);
   mlp_bwd_dw_kernel<<<items, kDwThreads, dw_smem_bytes(), st>>>(d);
+  prof_end_ext(pe, st);
   return check_cuda(cudaGetLastError(), "launch mlp_bwd_dw_kernel");
 }
 

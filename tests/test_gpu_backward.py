@@ -89,9 +89,13 @@ def test_render_backward_vs_explicit_chain(width, n):
     rgb0 = ops.render_forward(net, pts.to(dev), view.to(dev), nrm.to(dev), feats.to(dev))
     gate("render_forward_train_vs_forward", (rgb - rgb0).abs().max().item(), 5e-6)
     d_points, d_normals, d_feats, dw, db = ops.render_backward(net, save, rgb, g_rgb.to(dev))
-    gate("d_points_rel", _rel(d_points, dp_ref), G_DX)
-    gate("d_normals_rel", _rel(d_normals, dn_ref), G_DX)
-    gate("d_feats_rel", _rel(d_feats, df_ref), G_DX)
+    # ReLU kinks: a pre-activation within fp32 rounding of zero (a few per million units) has a different sign in the fp64
+    # chain than in the fp32 forward, which switches one hidden unit of one point on / off -- an O(1/sqrt(width)) change of
+    # that point's input gradients.  Per-point errors are therefore gated on the 99th percentile, the outliers are counted.
+    for name, got, ref in (("d_points", d_points, dp_ref), ("d_normals", d_normals, dn_ref), ("d_feats", d_feats, df_ref)):
+        row = (got.double().cpu() - ref).abs().max(dim=1).values / ref.abs().max().item()
+        gate(name + "_rel_q99", torch.quantile(row, 0.99).item(), G_DX)
+        gate(name + "_rows_above_gate", int((row > G_DX).sum()), max(1, n // 100))
     dvs, dgs, dbs = ops.weight_grads(net, dw, db, [v.float().to(dev) for v in vs], [x.float().to(dev) for x in gs])
     worst = 0.0
     for l in range(5):
