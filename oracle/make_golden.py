@@ -188,6 +188,35 @@ def case_tracer(ref, name, preset, H, W, n_images, training, seed):
     print(f"{name}: hits {int(nm.sum())}/{nm.numel()}")
 
 
+def case_featext(ref, name, seed, n, H, W):
+    """FeatExt (utils/my_utils.py:693-708) with SEEDED RANDOM weights and BatchNorm statistics under the reference's own
+    key names (mvsdf_b200.featext.B200FeatExt(seed) regenerates them; utils/vismvsnet.pt cannot travel to the GPU box).
+    The reference class loads that checkpoint in its constructor from a cwd-relative path with CUDA storages: it is
+    constructed under cwd = code/ with torch.load mapped to the CPU, then its state is overwritten."""
+    from mvsdf_b200.featext import B200FeatExt
+    mine = B200FeatExt(seed=seed)
+    sd = mine.state_dict()
+    cwd = os.getcwd()
+    orig_load = torch.load
+    try:
+        os.chdir(ref_shim.REFERENCE_CODE)
+        torch.load = lambda *a, **k: orig_load(*a, **{**k, "map_location": "cpu", "weights_only": False})
+        fe = ref.my_utils.FeatExt()
+    finally:
+        torch.load = orig_load
+        os.chdir(cwd)
+    res = fe.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys, res
+    fe.eval()
+    x = torch.randn(n, 3, H, W, generator=torch.Generator().manual_seed(seed + 100))
+    with torch.no_grad():
+        o8, o4, o2 = fe(x)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), meta_seed=seed, meta_shape=np.array([n, H, W]),
+                        meta_weights_sha=synth.state_dict_checksum({k: v for k, v in sd.items() if v.dtype.is_floating_point}),
+                        out_eighth=o8.numpy(), out_quarter=o4.numpy(), out_half=o2.numpy())
+    print("wrote", name, [tuple(t.shape) for t in (o8, o4, o2)], "max", float(o2.abs().max()))
+
+
 def main():
     """python -m oracle.make_golden [case-name ...]   (no names: every case)"""
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -209,6 +238,8 @@ def main():
         # in seconds: eval with 4 source views; training (tp = 0.5) with 2 images x 8 source views
         (case_forward, ("cfg2_shape_eval_w512", "w512", 28, 28, 1, 4, None, False, None), dict(seed=8)),
         (case_forward, ("cfg3_shape_train_w512", "w512", 48, 48, 2, 8, 192, True, 0.5), dict(seed=9)),
+        # row f4: the feature extractor with seeded random weights
+        (case_featext, ("featext_seed5",), dict(seed=5, n=2, H=48, W=64)),
     ]
     only = set(sys.argv[1:])
     for fn, args, kw in cases:

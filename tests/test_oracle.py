@@ -187,3 +187,29 @@ def test_e_trace_counts_are_the_reference_tracers_own_evaluations(training):
     assert torch.allclose(o_dists, r_dists, rtol=1e-6, atol=1e-6)
     # the reference evaluates the 100 sampler points of EVERY ray slot it gathered, in 100 000-point chunks: same count
     assert oc.total == n_evals[0], (oc, n_evals[0])
+
+
+def test_featext_oracle_matches_live_reference():
+    """Row f4: oracle/featext_oracle.py against the unmodified FeatExt (my_utils.py:693-708) with the checkpoint the reference
+    ships (utils/vismvsnet.pt) -- only where /root/reference exists."""
+    import os
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    from oracle import featext_oracle as FO
+    ref = ref_shim.load()
+    cwd, orig_load = os.getcwd(), torch.load
+    try:
+        os.chdir(ref_shim.REFERENCE_CODE)
+        torch.load = lambda *a, **k: orig_load(*a, **{**k, "map_location": "cpu", "weights_only": False})
+        fe = ref.my_utils.FeatExt()
+    finally:
+        torch.load = orig_load
+        os.chdir(cwd)
+    fe.eval()
+    x = torch.randn(1, 3, 40, 56, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = fe(x)
+        got = FO.featext_forward(fe.state_dict(), x)
+    for a, b in zip(got, want):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
