@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_tile_kernel(const MlpArgs 
   const long long group0 = blockIdx.x / CL;
   const long long group_stride = gridDim.x / CL;
   constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
+  if (n_tiles == 0) return;      // empty request list: nothing to set up (uniform over the grid)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {

@@ -93,6 +93,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
   const long long n_tiles = (n_pts + 2 * kPtsPerCta - 1) / (2 * kPtsPerCta);
   const long long pair0 = blockIdx.x >> 1;
   const long long pair_stride = gridDim.x >> 1;
+  // an empty request list (most back-off passes of the sphere tracer) costs a launch and nothing else: every CTA of every
+  // cluster leaves before barriers, TMEM or the cluster handshake are touched
+  if (n_tiles == 0) return;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {

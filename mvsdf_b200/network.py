@@ -467,12 +467,18 @@ class B200IDRNetwork(nn.Module):
         object_mask = object_mask_true if conf.use_mask else torch.ones_like(object_mask_true)
         B, N, _ = uv.shape
         R = B * N
-        sdf_net = self.implicit_network.packed()
-        rend_net = self.rendering_network.packed()
+        steps_dev = None
+        if not self.skip_min_sdf:
+            steps_dev = (steps01 if steps01 is not None else torch.empty(self.tracer_conf["n_steps"]).uniform_(0.0, 1.0))
+            steps_dev = steps_dev.to(device=dev, dtype=torch.float32).contiguous()
         with torch.no_grad():
-            ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics,
-                                                                  object_mask.to(torch.uint8).contiguous(), True, steps01)
-            sdf_out = ops.sdf_forward(sdf_net, points, ops.HEAD_SDF_ONLY)
+            targs = (uv, pose, intrinsics, object_mask.to(torch.uint8).contiguous(), steps_dev)
+            if self.use_graphs and R <= self.graph_max_rays:
+                raw = self._replay("trace", self._enqueue_trace, True, targs)
+            else:
+                raw = self._enqueue_trace(True, *targs)
+        sdf_net, rend_net = raw["sdf_net"], raw["rend_net"]
+        ray_dirs, cam_loc, dists, net_u8, points, sdf_out = (raw[k] for k in ("ray_dirs", "cam_loc", "dists", "net_u8", "points", "sdf_out"))
         network_object_mask = net_u8.bool()
         surface_mask = network_object_mask & object_mask
         idx = surface_mask.nonzero(as_tuple=False).squeeze(1)            # data-dependent size: one host sync, as in the reference
@@ -636,17 +642,27 @@ class B200IDRNetwork(nn.Module):
             raw["extra"], raw["g_extra"] = ops.sdf_value_grad(sdf_net, extra_pts, ops.HEAD_FULL)
         return raw
 
-    _GRAPH_OUT = ("ray_dirs", "cam_loc", "dists", "net_u8", "points", "sdf_out", "rgb_values", "surf_pts", "normals", "surf_head",
-                  "hit_index", "hit_offsets", "extra", "g_extra")
+    def _enqueue_trace(self, training, uv, pose, intrinsics, obj_u8, steps_dev, _unused=None):
+        """The no-grad head of a training forward with autograd (:192-203): weight packing, tracer, sdf_output of every ray.
+        Enqueue only -- capturable."""
+        sdf_net = self.implicit_network.packed()
+        rend_net = self.rendering_network.packed()
+        ray_dirs, cam_loc, dists, net_u8, points = self.trace(sdf_net, uv, pose, intrinsics, obj_u8, training, steps_dev)
+        sdf_out = ops.sdf_forward(sdf_net, points, ops.HEAD_SDF_ONLY)
+        return dict(sdf_net=sdf_net, rend_net=rend_net, ray_dirs=ray_dirs, cam_loc=cam_loc, dists=dists, net_u8=net_u8, points=points,
+                    sdf_out=sdf_out, counters=self.last_trace_counters)
 
-    def _replay_native(self, training, uv, pose, intrinsics, obj_u8, steps_dev, extra_pts):
-        """_enqueue_native through a CUDA graph captured once per (shapes, mode, tracer settings, parameter storage)."""
+    def _replay_native(self, training, *live):
+        return self._replay("native", self._enqueue_native, training, live)
+
+    def _replay(self, tag, fn, training, live):
+        """fn(training, *tensors) through a CUDA graph captured once per (shapes, mode, tracer settings, parameter storage)."""
         L = _lib.lib()
-        dev = uv.device
-        live = [uv, pose, intrinsics, obj_u8, steps_dev, extra_pts]
+        live = list(live)
+        dev = live[0].device
         pkey = tuple(p.data_ptr() for p in self.parameters())
         tkey = tuple(sorted(self.tracer_conf.items())) + (os.environ.get("IDR_USE_ENV", "0"), os.environ.get("IDR_RENDER", "0"))
-        key = (training, bool(self.skip_min_sdf), float(self.prefilter_tau), str(dev), pkey, tkey,
+        key = (tag, training, bool(self.skip_min_sdf), float(self.prefilter_tau), str(dev), pkey, tkey,
                tuple(None if t is None else (tuple(t.shape), t.dtype) for t in live))
         g = self._graphs.get(key)
         if g is None:
@@ -655,13 +671,13 @@ class B200IDRNetwork(nn.Module):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                self._enqueue_native(training, *static)
+                fn(training, *static)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             n0 = L.mvsdf_launch_count()
             with torch.cuda.graph(graph):
-                raw = self._enqueue_native(training, *static)
+                raw = fn(training, *static)
             g = dict(graph=graph, static=static, raw=raw, launches=L.mvsdf_launch_count() - n0)
             if len(self._graphs) >= 8:                       # bounded cache (e.g. tau widening creates new keys)
                 self._graphs.pop(next(iter(self._graphs)))
@@ -674,8 +690,10 @@ class B200IDRNetwork(nn.Module):
         self.graph_replays += 1
         raw = dict(g["raw"])
         self.last_trace_counters = raw["counters"]
+        for net in (raw["sdf_net"], raw["rend_net"]):        # the replay re-packed the weights without running pack()'s host side
+            net._t_valid = False
         # hand out copies: the graph's output buffers are overwritten by the next replay
-        for k in self._GRAPH_OUT:
-            if k in raw and raw[k] is not None:
-                raw[k] = raw[k].clone()
+        for k, v in raw.items():
+            if isinstance(v, torch.Tensor) and k != "counters":
+                raw[k] = v.clone()
         return raw
