@@ -184,6 +184,7 @@ def run_ours(args):
     host = pin({k: scene[k] for k in IN_KEYS + GT_KEYS})
     resident = {k: host[k].to(dev) for k in IN_KEYS + GT_KEYS}
 
+    @torch.no_grad()          # the metric is the forward path; the training step (backward + Adam) is --workload train32k
     def step(inputs):
         kw = dict(steps01=steps01, eik_points=eik) if cfg["training"] else {}
         out = model({k: inputs[k] for k in IN_KEYS}, tp if cfg["training"] else None, **kw)
