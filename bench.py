@@ -84,9 +84,10 @@ def ncu_traffic(workload, tau):
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period: float = 1.0):
         super().__init__(daemon=True)
         self.gpu = gpu_index
+        self.period = period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop_evt = threading.Event()
 
@@ -105,7 +106,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(self.period)
 
     def stop(self):
         self._stop_evt.set()
@@ -201,10 +202,13 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(resident)
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    # clocks / throttle reasons of the timed region: one nvidia-smi query per second on rank 0's GPU (every query takes a
+    # driver-wide lock for tens of ms; with one sampler per rank at 5 Hz the ranks' launch threads stalled each other)
+    clocks = ClockSampler(local, args.clock_period) if (rank == 0 and args.clock_period > 0) else None
+    if clocks:
+        clocks.start()
     launches0 = L.mvsdf_launch_count()
-    L.mvsdf_profile_enable(1)
+    L.mvsdf_profile_enable(0 if args.no_profile else 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -213,7 +217,7 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     ms_local = ms_total / args.steps
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     launches = L.mvsdf_launch_count() - launches0
     import ctypes
     ms_kind = (ctypes.c_float * 8)()          # MVSDF_PROFILE_KINDS
@@ -310,9 +314,19 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(cfg, scene, sd, budget_s=args.cpu_budget)
         try:
+            # the reference's own thread setting: torch.set_num_threads(1) (training/idr_train.py:21)
+            one = cpu_reference_sample(cfg, scene, sd, budget_s=min(10.0, args.cpu_budget), threads=1)
+            cpu_base["one_thread"] = {"value": one["value"], "unit": "rays/s", "cores": 1, "sample": one["sample"]}
+        except Exception as e:
+            cpu_base["one_thread"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        try:
             cpu_base["torch_cuda_port"] = torch_cuda_port_sample(cfg, scene, sd, dev)
         except Exception as e:                      # a baseline, never a reason to lose the bench line
             cpu_base["torch_cuda_port"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        try:
+            cpu_base["torch_cuda_port_cfg3_train"] = torch_cuda_port_cfg3_train(dev)
+        except Exception as e:
+            cpu_base["torch_cuda_port_cfg3_train"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         line = {
@@ -617,6 +631,37 @@ def torch_cuda_port_sample(cfg, scene, sd, dev, n_sample=240000):
                       "(eager PyTorch fp32, TF32 off)"}
 
 
+def torch_cuda_port_cfg3_train(dev):
+    """the reference algorithm as eager PyTorch-CUDA ops (the oracle port on cuda:0) at config 3 --
+    2 x 4096 rays, 8 source views, train-mode forward (tp = 0.5) + feat loss + rgb L1 -- with and without
+    minimal_sdf_points (ray_tracing.py:280-308, 62 % of the reference's evaluations, read by no MVSDF loss)."""
+    from oracle import mvsdf_oracle as O
+    cfg = WORKLOADS["cfg3"]
+    scene, sd = make_inputs(cfg, 0)
+    sc = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in scene.items()}
+    sw, rw = O.sdf_weights(sd).to(dev), O.render_weights(sd).to(dev)
+    R = scene["uv"].shape[0] * scene["uv"].shape[1]
+    g = torch.Generator().manual_seed(1234)
+    steps01 = torch.rand(100, generator=g).to(dev)
+    eik = (torch.rand(R // 2, 3, generator=g) * 2 - 1).to(dev)
+    res = {}
+    for skip in (False, True):
+        def one():
+            out = O.idr_forward(sw, rw, sc, 0.5, True, steps01=steps01, eik_points=eik, skip_min_sdf=skip)
+            ls = O.hot_path_losses(out, sc, 0.5)
+            return float(ls["rgb_loss"].detach())
+        one()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / 3
+        res["skip_min_sdf" if skip else "with_min_sdf"] = {"rays_per_s": R / dt, "ms_per_step": dt * 1e3}
+    res["sample"] = f"{R} rays (cfg3), train-mode forward + feat loss + rgb L1, oracle port on cuda:0 (eager PyTorch fp32), 3 timed steps"
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -680,6 +725,8 @@ def main():
     ap.add_argument("--skip-min-sdf", type=int, default=0)
     ap.add_argument("--prefilter-tau", type=float, default=None, help="override B200IDRNetwork.prefilter_tau (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=1.0, help="seconds between nvidia-smi clock samples on rank 0 (0 = off)")
+    ap.add_argument("--no-profile", action="store_true", help="diagnostic: no per-launch CUDA events in the timed region")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     claim_stdout()
