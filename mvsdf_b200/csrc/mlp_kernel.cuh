@@ -150,17 +150,35 @@ __device__ __forceinline__ float softplus100_scaled_grad(float z, float& sig) {
 // rounding, so the threshold of nn.Softplus needs no special case.
 constexpr float kSpT = 100.0f * 1.4426950408889634f;                  // t = kSpT * z
 constexpr float kSpC = kActScale * 0.6931471805599453f * 0.01f;
+// lg2(1 + e), e in (0, 1].  Default: the MUFU unit.  -DMVSDF_SOFTPLUS_POLY: e * P6(e) on the FMA pipe (minimax fit, max error
+// 3.1e-7, i.e. 2e-9 on the activation -- below its fp32 rounding -- and exactly 0 at e = 0).  Round-2 experiment: the idea was
+// that the epilogue stage E_0, which the tensor pipe waits for at every layer, is SFU-bound (two MUFU ops per element at
+// 16 lanes / clock / SM).  Measured on the 378 880-point probe: 3.25 ms against 3.18 ms with MUFU, cfg2 step 615.8 ms against
+// 606.9 ms -- the six extra FMAs cost more issue slots (shared with the UMMA issuer warp) than the MUFU op they replace.
+// Rejected; kept for A/B.
+#ifdef MVSDF_SOFTPLUS_POLY
+__device__ __forceinline__ float lg2_1p(float e) {
+  float p = fmaf(e, 0.0155299071f, -0.0795576957f);
+  p = fmaf(p, e, 0.194294275f);
+  p = fmaf(p, e, -0.325901943f);
+  p = fmaf(p, e, 0.473553401f);
+  p = fmaf(p, e, -0.720585467f);
+  p = fmaf(p, e, 1.44266783f);
+  return p * e;
+}
+#else
+__device__ __forceinline__ float lg2_1p(float e) { return ptx::lg2_approx(1.0f + e); }
+#endif
 __device__ __forceinline__ float softplus_t_scaled(float t) {
   const float e = ptx::ex2_approx(-fabsf(t));
-  return (fmaxf(t, 0.0f) + ptx::lg2_approx(1.0f + e)) * kSpC;
+  return (fmaxf(t, 0.0f) + lg2_1p(e)) * kSpC;
 }
 // same, also returning d softplus / dz = sigmoid(100 z) = 1/(1+2^-t)
 __device__ __forceinline__ float softplus_t_scaled_grad(float t, float& sig) {
   const float e = ptx::ex2_approx(-fabsf(t));
-  const float ope = 1.0f + e;
-  const float r = ptx::rcp_approx(ope);
+  const float r = ptx::rcp_approx(1.0f + e);
   sig = t >= 0.0f ? r : e * r;
-  return (fmaxf(t, 0.0f) + ptx::lg2_approx(ope)) * kSpC;
+  return (fmaxf(t, 0.0f) + lg2_1p(e)) * kSpC;
 }
 // hi/lo split with the residual computed by mixed-precision FMAs (y - float(h) = h * (-1) + y, SASS: FHFMA)
 __device__ __forceinline__ void pack_split_fh(float y0, float y1, uint32_t& hi2, uint32_t& lo2) {

