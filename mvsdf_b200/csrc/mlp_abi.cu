@@ -355,7 +355,8 @@ const char* mvsdf_last_error(void) { return g_err; }
 
 mvsdf_net* mvsdf_sdf_net_create(int width, int n_hidden, int skip_layer, int n_freqs, int feature_size) {
   const int d0 = 3 + 6 * n_freqs;
-  if (width < 64 || width > 512 || width % 32 != 0 || n_hidden < 2 || n_hidden + 2 > kMaxLayers || n_freqs != 6 ||
+  // widths are whole 128-row output tiles: a partial tile would write activation rows beyond the operand buffer
+  if (width < 128 || width > 512 || width % 128 != 0 || n_hidden < 2 || n_hidden + 2 > kMaxLayers || n_freqs != 6 ||
       skip_layer < 1 || skip_layer >= n_hidden || width - d0 <= 0 || feature_size < 1 ||
       ceil_div(feature_size + 2, kTileM) * kTileN > kTmemCols) {
     fail(MVSDF_ERR_INVALID, "unsupported SDF net: width=%d hidden=%d skip=%d freqs=%d feat=%d", width, n_hidden,
@@ -405,7 +406,7 @@ mvsdf_net* mvsdf_sdf_net_create(int width, int n_hidden, int skip_layer, int n_f
 }
 
 mvsdf_net* mvsdf_render_net_create(int width, int n_hidden, int n_freqs_view, int feature_size) {
-  if (width < 64 || width > 512 || width % 32 != 0 || n_hidden < 1 || n_hidden + 1 > kMaxLayers || n_freqs_view != 4 ||
+  if (width < 128 || width > 512 || width % 128 != 0 || n_hidden < 1 || n_hidden + 1 > kMaxLayers || n_freqs_view != 4 ||
       feature_size < 1) {
     fail(MVSDF_ERR_INVALID, "unsupported rendering net: width=%d hidden=%d freqs=%d feat=%d", width, n_hidden,
          n_freqs_view, feature_size);

@@ -132,7 +132,7 @@ class ImplicitNetwork(_PackedMlp):
         dims = list(dims)
         if d_in != 3 or d_out != 1 or multires != 6 or not weight_norm or len(set(dims)) != 1 or len(skip_in) != 1:
             raise _lib.MvsdfError("mvsdf_b200 supports the shipped SDF architecture family: d_in=3, d_out=1, "
-                                  "multires=6, equal hidden widths, one skip layer, weight_norm=True")
+                                  "multires=6, equal hidden widths (128, 256, 384 or 512), one skip layer, weight_norm=True")
         self.width = dims[0]
         self.n_hidden = len(dims)
         self.feature_vector_size = feature_vector_size

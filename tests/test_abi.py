@@ -35,7 +35,8 @@ def test_plans_and_argument_validation(lib):
     # 8 hidden layers + two heads, fp16 hi/lo tiles: a bit over 2 x 2 bytes per padded weight
     assert 8_000_000 < lib.mvsdf_net_packed_bytes(h) < 10_000_000
     lib.mvsdf_net_destroy(h)
-    assert not lib.mvsdf_sdf_net_create(100, 8, 4, 6, 256)          # width must be a multiple of 32
+    assert not lib.mvsdf_sdf_net_create(100, 8, 4, 6, 256)          # width must be a multiple of 128 (whole output tiles)
+    assert not lib.mvsdf_sdf_net_create(320, 8, 4, 6, 256)
     assert b"unsupported" in lib.mvsdf_last_error()
     assert not lib.mvsdf_render_net_create(512, 4, 3, 256)
     r = lib.mvsdf_render_net_create(256, 4, 4, 256)
