@@ -72,10 +72,10 @@ def load_peaks():
 
 
 def ncu_traffic(workload, tau):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01/dram_traffic_cfg2_v7.json:
-    dram__bytes_read.sum + dram__bytes_write.sum summed over the step's exact + screening SDF launches / their number).
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r02/dram_traffic_cfg2_r2.json:
+    dram__bytes_read.sum + dram__bytes_write.sum summed over the exact + screening SDF launches / their number).
     It cannot be measured live; null for configurations that were not captured."""
-    p = os.path.join(ROOT, "profiles", "r01", "dram_traffic_cfg2_v7.json")
+    p = os.path.join(ROOT, "profiles", "r02", "dram_traffic_cfg2_r2.json")
     if workload != "cfg2" or abs(tau - 0.002) > 1e-9 or not os.path.exists(p):
         return None
     return json.load(open(p))["dram_bytes_per_launch"]

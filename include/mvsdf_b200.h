@@ -268,10 +268,12 @@ int mvsdf_sdf_backward(const mvsdf_net* net, const void* packed_t, const float* 
 int mvsdf_render_forward_train(const mvsdf_net* net, const void* packed, const float* points, const float* view_dirs,
                                const float* normals, const float* features, int64_t n, size_t save_bytes, void* save, float* out_rgb,
                                void* stream);
-/* rgb [n,3] = the forward output (tanh'), g_rgb [n,3] = dL/d rgb; d_points / d_normals [n,3], d_feats [n,F] optional. */
+/* rgb [n,3] = the forward output (tanh'), g_rgb [n,3] = dL/d rgb; d_points / d_normals [n,3], d_feats [n,F] optional;
+ * d_view [n,3] optional (needs view_dirs [n,3], the forward's input): only trained camera poses make the view direction a
+ * function of parameters (utils/rend_util.py:49-57, train_cameras=True). */
 int mvsdf_render_backward(const mvsdf_net* net, const void* packed_t, int64_t n, const void* save, const float* rgb, const float* g_rgb,
-                          size_t workspace_bytes, void* workspace, float* d_points, float* d_normals, float* d_feats, float* out_dw,
-                          float* out_db, void* stream);
+                          const float* view_dirs, size_t workspace_bytes, void* workspace, float* d_points, float* d_normals,
+                          float* d_feats, float* d_view, float* out_dw, float* out_db, void* stream);
 /* *_host: HOST arrays of device pointers, one per source layer lin{l} (like mvsdf_pack_weights). */
 int mvsdf_weight_grads(const mvsdf_net* net, const float* dw, const float* db, const float* const* weight_v_host,
                        const float* const* weight_g_host, float* const* out_dv_host, float* const* out_dg_host,

@@ -70,7 +70,7 @@ def _declare(lib):
     lib.mvsdf_render_forward_train.restype = c_int
     lib.mvsdf_render_forward_train.argtypes = [P, P, P, P, P, P, c_int64, c_size_t, P, P, P]
     lib.mvsdf_render_backward.restype = c_int
-    lib.mvsdf_render_backward.argtypes = [P, P, c_int64, P, P, P, c_size_t, P, P, P, P, P, P, P]
+    lib.mvsdf_render_backward.argtypes = [P, P, c_int64, P, P, P, P, c_size_t, P, P, P, P, P, P, P, P]
     lib.mvsdf_weight_grads.restype = c_int
     lib.mvsdf_weight_grads.argtypes = [P, P, P, POINTER(P), POINTER(P), POINTER(P), POINTER(P), POINTER(P), P]
     lib.mvsdf_adam_step.restype = c_int

@@ -80,29 +80,30 @@ class SdfEval(torch.autograd.Function):
 
 
 class RenderEval(torch.autograd.Function):
-    """rgb = RenderEval.apply(net, points, normals, view, feats, *params).  The view direction is a constant of the ray
-    (train_cameras=False): no gradient is produced for it."""
+    """rgb = RenderEval.apply(net, points, normals, view, feats, *params).  The gradient w.r.t. the view direction is only
+    produced when it is asked for (trained camera poses; otherwise the view direction is a constant of the ray)."""
 
     @staticmethod
     def forward(ctx, net: ops.PackedNet, points, normals, view, feats, *params):
         rgb, save = ops.render_forward_train(net, points, view, normals, feats)
         ctx.net = net
         ctx.save = save
-        ctx.save_for_backward(rgb, *params)
+        ctx.save_for_backward(rgb, view, *params)
         return rgb
 
     @staticmethod
     def backward(ctx, g_rgb):
-        rgb, *params = ctx.saved_tensors
+        rgb, view, *params = ctx.saved_tensors
         net = ctx.net
         needs = ctx.needs_input_grad
         if rgb.shape[0] == 0:
-            return (None, None, None, None, None, *[torch.zeros_like(p) if nd else None for p, nd in zip(params, needs[5:])])
-        d_points, d_normals, d_feats, dw, db = ops.render_backward(net, ctx.save, rgb, g_rgb)
+            zin = [torch.zeros_like(t) if nd else None for t, nd in zip((rgb, rgb, view), needs[1:4])]
+            return (None, *zin, None, *[torch.zeros_like(p) if nd else None for p, nd in zip(params, needs[5:])])
+        d_points, d_normals, d_feats, d_view, dw, db = ops.render_backward(net, ctx.save, rgb, g_rgb, view if needs[3] else None)
         vs, gs, _ = _param_lists(params)
         dvs, dgs, dbs = ops.weight_grads(net, dw, db, vs, gs)
-        return (None, d_points if needs[1] else None, d_normals if needs[2] else None, None, d_feats if needs[4] else None,
-                *_interleave(dvs, dgs, dbs, needs[5:]))
+        return (None, d_points if needs[1] else None, d_normals if needs[2] else None, d_view if needs[3] else None,
+                d_feats if needs[4] else None, *_interleave(dvs, dgs, dbs, needs[5:]))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

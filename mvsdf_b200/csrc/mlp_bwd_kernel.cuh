@@ -40,7 +40,7 @@ struct BwdArgs {
   long long n;
   const float* gscale;         // [2] device: {S, 1/S}
   // forward state
-  const float* x;              // [n,3] SDF: points (PE derivatives for dx); render: unused
+  const float* x;              // [n,3] SDF: points (PE derivatives for dx); render: view directions (only with dx)
   const uint8_t* save;         // saved layer inputs of the forward pass
   long long save_off[kMaxLayers];    // by FORWARD layer index
   int save_kc[kMaxLayers];           // feature blocks of that image
@@ -54,7 +54,7 @@ struct BwdArgs {
   int dz_kc[kMaxLayers];
   float* db;                   // bias gradients (scaled by S), plan coordinates: db + db_off[l] + row
   int db_off[kMaxLayers];
-  float* dx;                   // SDF: [n,3] accumulated with atomics (pre-zeroed), or nullptr
+  float* dx;                   // SDF: dL/dx [n,3]; render: dL/d view [n,3]; accumulated with atomics (pre-zeroed), or nullptr
   float* d_points;             // render: [n,3]
   float* d_normals;            // render: [n,3]
   float* d_feats;              // render: [n, feat_size]
@@ -355,6 +355,21 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
                     const float val = d[j] * invS;
                     if (f < 3) {
                       if (a.d_points) a.d_points[gp * 3 + f] = val;
+                    } else if (f < 30) {
+                      // PE4(view) rows: chained through PE' into the view direction (only needed when the camera poses are
+                      // trained, rend_util.py:49-57: the view direction then depends on the pose parameters)
+                      if (a.dx) {
+                        const int k = f - 3;
+                        const int coord = k < 3 ? k : (k - 3) % 3;
+                        float p1 = 1.0f;
+                        if (k >= 3) {
+                          const float fr = (float)(1 << ((k - 3) / 6));
+                          float sn, cs;
+                          sincosf(__ldg(a.x + gp * 3 + coord) * fr, &sn, &cs);
+                          p1 = ((k - 3) % 6) >= 3 ? -fr * sn : fr * cs;
+                        }
+                        atomicAdd(a.dx + gp * 3 + coord, val * p1);
+                      }
                     } else if (f >= 30 && f < 33) {
                       if (a.d_normals) a.d_normals[gp * 3 + (f - 30)] = val;
                     } else if (f >= 33 && f < 33 + F) {

@@ -533,12 +533,13 @@ int mvsdf_render_forward_train(const mvsdf_net* net, const void* packed, const f
 }
 
 int mvsdf_render_backward(const mvsdf_net* net, const void* packed_t, int64_t n, const void* save, const float* rgb, const float* g_rgb,
-                          size_t workspace_bytes, void* workspace, float* d_points, float* d_normals, float* d_feats, float* out_dw,
-                          float* out_db, void* stream) {
+                          const float* view_dirs, size_t workspace_bytes, void* workspace, float* d_points, float* d_normals,
+                          float* d_feats, float* d_view, float* out_dw, float* out_db, void* stream) {
   if (!net || net->plan.kind != NET_RENDER) return fail(MVSDF_ERR_INVALID, "expected a rendering net plan");
   if (!packed_t || !save || !rgb || !g_rgb || !workspace || !out_dw || !out_db || n <= 0)
     return fail(MVSDF_ERR_INVALID, "mvsdf_render_backward: null argument / empty batch");
-  return run_backward<NET_RENDER, 0>(net, packed_t, nullptr, n, save, g_rgb, nullptr, rgb, workspace_bytes, workspace, nullptr, d_points,
+  if (d_view && !view_dirs) return fail(MVSDF_ERR_INVALID, "mvsdf_render_backward: d_view needs view_dirs");
+  return run_backward<NET_RENDER, 0>(net, packed_t, view_dirs, n, save, g_rgb, nullptr, rgb, workspace_bytes, workspace, d_view, d_points,
                                      d_normals, d_feats, out_dw, out_db, static_cast<cudaStream_t>(stream));
 }
 

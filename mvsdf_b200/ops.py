@@ -212,8 +212,9 @@ def render_forward_train(net: PackedNet, points, view_dirs, normals, features):
     return rgb, save
 
 
-def render_backward(net: PackedNet, save: torch.Tensor, rgb: torch.Tensor, g_rgb: torch.Tensor):
-    """Reverse sweep + dW GEMM of the rendering net: (d_points, d_normals, d_feats, dw, db)."""
+def render_backward(net: PackedNet, save: torch.Tensor, rgb: torch.Tensor, g_rgb: torch.Tensor, view_dirs: Optional[torch.Tensor] = None):
+    """Reverse sweep + dW GEMM of the rendering net: (d_points, d_normals, d_feats, d_view or None, dw, db); d_view is
+    produced when view_dirs is given (trained camera poses)."""
     L = _lib.lib()
     rgb, g_rgb = _f32(rgb), _f32(g_rgb)
     n = rgb.shape[0]
@@ -225,12 +226,14 @@ def render_backward(net: PackedNet, save: torch.Tensor, rgb: torch.Tensor, g_rgb
     d_points = torch.empty(n, 3, dtype=torch.float32, device=dev)
     d_normals = torch.empty(n, 3, dtype=torch.float32, device=dev)
     d_feats = torch.empty(n, F, dtype=torch.float32, device=dev)
+    view = None if view_dirs is None else _f32(view_dirs)
+    d_view = None if view is None else torch.empty(n, 3, dtype=torch.float32, device=dev)
     ws_bytes = L.mvsdf_train_workspace_bytes(net.handle, n, 0)
     ws = _scratch("render_bwd", ws_bytes, dev)
-    _lib.check(L.mvsdf_render_backward(net.handle, _lib.ptr(net.blob_t), n, _lib.ptr(save), _lib.ptr(rgb), _lib.ptr(g_rgb), ws.numel(),
-                                       _lib.ptr(ws), _lib.ptr(d_points), _lib.ptr(d_normals), _lib.ptr(d_feats), _lib.ptr(dw),
-                                       _lib.ptr(db), _stream(dev)))
-    return d_points, d_normals, d_feats, dw, db
+    _lib.check(L.mvsdf_render_backward(net.handle, _lib.ptr(net.blob_t), n, _lib.ptr(save), _lib.ptr(rgb), _lib.ptr(g_rgb), _lib.ptr(view),
+                                       ws.numel(), _lib.ptr(ws), _lib.ptr(d_points), _lib.ptr(d_normals), _lib.ptr(d_feats),
+                                       _lib.ptr(d_view), _lib.ptr(dw), _lib.ptr(db), _stream(dev)))
+    return d_points, d_normals, d_feats, d_view, dw, db
 
 
 def weight_grads(net: PackedNet, dw: torch.Tensor, db: torch.Tensor, vs: List[torch.Tensor], gs: List[Optional[torch.Tensor]]):

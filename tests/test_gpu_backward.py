@@ -85,16 +85,17 @@ def test_render_backward_vs_explicit_chain(width, n):
     vs = [sd[f"rendering_network.lin{l}.weight_v"].double() for l in range(5)]
     gs = [sd[f"rendering_network.lin{l}.weight_g"].double() for l in range(5)]
     bs = [sd[f"rendering_network.lin{l}.bias"].double() for l in range(5)]
-    dp_ref, dn_ref, _, df_ref, dv_ref, dg_ref, db_ref = S.render_backward(pts.double(), nrm.double(), view.double(), feats.double(),
+    dp_ref, dn_ref, dview_ref, df_ref, dv_ref, dg_ref, db_ref = S.render_backward(pts.double(), nrm.double(), view.double(), feats.double(),
                                                                          vs, gs, bs, 4, g_rgb.double())
     rgb, save = ops.render_forward_train(net, pts.to(dev), view.to(dev), nrm.to(dev), feats.to(dev))
     rgb0 = ops.render_forward(net, pts.to(dev), view.to(dev), nrm.to(dev), feats.to(dev))
     gate("render_forward_train_vs_forward", (rgb - rgb0).abs().max().item(), 5e-6)
-    d_points, d_normals, d_feats, dw, db = ops.render_backward(net, save, rgb, g_rgb.to(dev))
+    d_points, d_normals, d_feats, d_view, dw, db = ops.render_backward(net, save, rgb, g_rgb.to(dev), view.to(dev))
     # ReLU kinks: a pre-activation within fp32 rounding of zero (a few per million units) has a different sign in the fp64
     # chain than in the fp32 forward, which switches one hidden unit of one point on / off -- an O(1/sqrt(width)) change of
     # that point's input gradients.  Per-point errors are therefore gated on the 99th percentile, the outliers are counted.
-    for name, got, ref in (("d_points", d_points, dp_ref), ("d_normals", d_normals, dn_ref), ("d_feats", d_feats, df_ref)):
+    for name, got, ref in (("d_points", d_points, dp_ref), ("d_normals", d_normals, dn_ref), ("d_feats", d_feats, df_ref),
+                           ("d_view", d_view, dview_ref)):
         row = (got.double().cpu() - ref).abs().max(dim=1).values / ref.abs().max().item()
         gate(name + "_rel_q99", torch.quantile(row, 0.99).item(), G_DX)
         gate(name + "_rows_above_gate", int((row > G_DX).sum()), max(1, n // 100))
