@@ -237,8 +237,8 @@ class RenderingNetwork(_PackedMlp):
 PREFILTER_TAU_MAX = 2.5e-2
 def _quaternion_pose(pose7: torch.Tensor) -> torch.Tensor:
     """rend_util.get_camera_params :49-54: [B,7] = (quaternion r,i,j,k ; camera centre) -> cam->world [B,4,4].  O(B) host
-    glue in front of ray_setup_kernel; the value path only -- gradients w.r.t. trained cameras (train_cameras=True,
-    exp_runner.py:40 default False) are not produced."""
+    glue in front of ray_setup_kernel (the tracer's value path); gradients w.r.t. trained cameras come from
+    _camera_rays_autograd on the surface rays."""
     q = torch.nn.functional.normalize(pose7[:, :4].detach().to(torch.float32), dim=1)
     r, i, j, k = q.unbind(dim=1)
     R = torch.stack([1 - 2 * (j * j + k * k), 2 * (j * i - k * r), 2 * (i * k + r * j),
@@ -248,6 +248,31 @@ def _quaternion_pose(pose7: torch.Tensor) -> torch.Tensor:
     p[:, :3, :3] = R
     p[:, :3, 3] = pose7[:, 4:].detach().to(torch.float32)
     return p.contiguous()
+
+
+def _camera_rays_autograd(uv_sel: torch.Tensor, b_idx: torch.Tensor, pose: torch.Tensor, intrinsics: torch.Tensor):
+    """rend_util.get_camera_params (:48-75) + lift (:87-100) for SELECTED rays, as differentiable torch ops: unit directions and
+    camera centres as functions of the pose parameters ([B,7] quaternion + centre, or [B,4,4]).  Only used with trained camera
+    poses (train_cameras=True, sample_network.py:15-19): the surface rays of a batch, O(M) elementwise work -- the tracer
+    itself stays native and gradient-free, like the reference's (no_grad, :192-198)."""
+    if pose.shape[1] == 7:
+        q = torch.nn.functional.normalize(pose[:, :4], dim=1)
+        r, i, j, k = q.unbind(dim=1)
+        R = torch.stack([1 - 2 * (j * j + k * k), 2 * (j * i - k * r), 2 * (i * k + r * j),
+                         2 * (j * i + k * r), 1 - 2 * (i * i + k * k), 2 * (j * k - i * r),
+                         2 * (k * i - j * r), 2 * (j * k + i * r), 1 - 2 * (i * i + j * j)], dim=1).view(-1, 3, 3)
+        c = pose[:, 4:]
+    else:
+        R, c = pose[:, :3, :3], pose[:, :3, 3]
+    K = intrinsics[b_idx]
+    fx, fy, cx, cy, sk = K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2], K[:, 0, 1]
+    x, y = uv_sel[:, 0] + 0.5, uv_sel[:, 1] + 0.5
+    xl = (x - cx + cy * sk / fy - sk * y / fy) / fx
+    yl = (y - cy) / fy
+    cam = torch.stack([xl, yl, torch.ones_like(xl)], dim=-1)                       # z = 1
+    cs = c[b_idx]
+    world = (R[b_idx] * cam.unsqueeze(1)).sum(-1) + cs                            # p @ [x, y, 1, 1]
+    return torch.nn.functional.normalize(world - cs, dim=1), cs
 
 
 DEFAULT_PREFILTER_TAU = 2.0e-3     # screening error (tools/diag_prefilter.py): max 9.6e-4 over the unit cube, 4e-4 near the surface; the guard trips at tau/2
@@ -461,6 +486,7 @@ class B200IDRNetwork(nn.Module):
         assert train_progress is not None
         uv, pose, intrinsics = ops._f32(input["uv"]), ops._f32(input["pose"]), ops._f32(input["intrinsics"])
         dev = uv.device
+        pose_param = input["pose"] if (torch.is_tensor(input["pose"]) and input["pose"].requires_grad) else None   # train_cameras
         if pose.shape[1] == 7:
             pose = _quaternion_pose(pose)
         object_mask_true = input["object_mask"].reshape(-1).to(device=dev, dtype=torch.bool)
@@ -488,6 +514,12 @@ class B200IDRNetwork(nn.Module):
             return self._redo_exact(self._forward_autograd, input, train_progress, steps01, eik_points, dsurf_rand)
         x_s, t_s, d_s = points[idx], dists[idx].unsqueeze(-1), ray_dirs[idx]
         c_s = cam_loc.unsqueeze(1).expand(B, N, 3).reshape(-1, 3)[idx]
+        if pose_param is not None:
+            # trained camera poses (rend_util.py:49-57, sample_network.py:15-19): the surface rays' directions and centres --
+            # and with them x_s, x_diff and the view direction -- become functions of the pose parameters
+            d_s, c_s = _camera_rays_autograd(uv.reshape(-1, 2)[idx], torch.div(idx, N, rounding_mode="floor"),
+                                             pose_param.to(device=dev, dtype=torch.float32), intrinsics)
+            x_s = c_s + t_s * d_s
         sdf_p = [t for lin in self.implicit_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
         rend_p = [t for lin in self.rendering_network._layers() for t in (lin.weight_v, lin.weight_g, lin.bias)]
 

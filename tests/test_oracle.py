@@ -213,3 +213,37 @@ def test_featext_oracle_matches_live_reference():
         got = FO.featext_forward(fe.state_dict(), x)
     for a, b in zip(got, want):
         assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
+
+
+def test_live_reference_pose_gradients_match_oracle():
+    """train_cameras=True (utils/rend_util.py:49-57, model/sample_network.py:15-19): gradients of the hot-path losses w.r.t. a
+    [B,7] quaternion pose, reference vs restatement -- the pin for B200IDRNetwork's pose-gradient path (tests/test_gpu_autograd.py)."""
+    ref = ref_shim.load()
+    from mvsdf_b200 import synth
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    model = ref.idr.IDRNetwork(ref_shim.DictConf(ref_shim.model_conf(64)))
+    model.load_state_dict(sd)
+    scene = synth.make_scene(16, 16, n_images=2, n_src=2, n_rays=128, seed=9)
+    pose7 = _pose7_from_matrix(scene["pose"])
+    model.train()
+    torch.manual_seed(7)
+    p_ref = pose7.clone().requires_grad_(True)
+    with ref_shim.quiet():
+        r = model({"uv": scene["uv"].clone(), "pose": p_ref, "intrinsics": scene["intrinsics"].clone(),
+                   "object_mask": scene["object_mask"].clone()}, 0.3)
+        lm = ref.loss.IDRLoss()
+        r_feat = lm.get_feat_loss_corr(r["diff_surf_pts"], None, scene["feat"], scene["cam"], scene["feat_src"],
+                                       scene["src_cams"], scene["size"][:1], scene["center"][:1],
+                                       r["network_object_mask"], r["object_mask"])
+        r_rgb = lm.get_rgb_loss(r["rgb_values"], scene["rgb"], r["network_object_mask"], r["object_mask"])
+        r_eik = lm.get_eikonal_loss(r["grad_theta"])
+    (r_rgb + r_feat + r_eik).backward()
+    torch.manual_seed(7)
+    p_o = pose7.clone().requires_grad_(True)
+    inp = dict(scene)
+    inp["pose"] = p_o
+    o = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), inp, 0.3, True)
+    losses = O.hot_path_losses(o, scene, 0.3)
+    (losses["rgb_loss"] + losses["feat_loss"] + losses["eikonal_loss"]).backward()
+    assert p_ref.grad is not None and float(p_ref.grad.abs().max()) > 0
+    assert torch.allclose(p_o.grad, p_ref.grad, rtol=2e-3, atol=1e-6 * float(p_ref.grad.abs().max())), (p_o.grad, p_ref.grad)
