@@ -114,3 +114,54 @@ def test_dense_grid_matches_oracle_on_a_subsample():
         ref = O.sdf_mlp(pts.double(), w64)[:, 0]
     got = vol[iy.reshape(-1), ix.reshape(-1), iz.reshape(-1)].cpu().double()
     assert (got - ref).abs().max().item() < TOL_SDF
+
+
+@pytest.mark.parametrize("width,n", [(128, 3000), (384, 100), (384, 40000), (128, 40000)])
+def test_other_widths_forward_render_and_backward(width, n):
+    """Hidden widths 128 and 384 (the architecture family is "multiples of 128 up to 512"): 384 has an odd number of 128-row
+    output tiles (a half-empty CTA-pair tile, a 256 + 128 split of the K dimension), 128 a single one.  Small counts take
+    the single-CTA kernel, large ones the CTA-pair kernel; the native backward runs on top."""
+    from mvsdf_b200 import ops
+    from oracle import backward_spec as S
+    dev = torch.device("cuda:0")
+    sd = synth.make_state_dict(width=width, seed=3, perturb=0.05, pe_noise=0.003, bias=0.6)
+    sdf = ops.PackedNet("sdf", width, 8).pack_state_dict(sd, "implicit_network", dev)
+    rend = ops.PackedNet("render", width, 4, n_freqs=4).pack_state_dict(sd, "rendering_network", dev)
+    gen = torch.Generator().manual_seed(n + width)
+    x = torch.rand(n, 3, generator=gen) * 1.6 - 0.8
+    m = min(n, 1024)
+    idx = torch.randperm(n, generator=gen)[:m]
+    w64 = O.sdf_weights(sd, dtype=torch.float64)
+    with torch.no_grad():
+        ref64 = O.sdf_mlp(x[idx].double(), w64)
+    gref = O.sdf_gradient(x[idx].double(), w64)
+    full, grad = ops.sdf_value_grad(sdf, x.to(dev), ops.HEAD_FULL)
+    assert (full.cpu()[idx].double() - ref64).abs().max().item() < TOL_SDF
+    assert (grad.cpu()[idx].double() - gref).abs().max().item() < TOL_GRAD
+    s = ops.sdf_forward(sdf, x.to(dev), ops.HEAD_SDF_ONLY)
+    assert (s.cpu()[idx].double() - ref64[:, 0]).abs().max().item() < TOL_SDF
+    scr = ops.sdf_forward(sdf, x.to(dev), ops.HEAD_SDF_SCREEN)
+    assert (scr - s).abs().max().item() < 2e-3
+    # rendering net
+    view = torch.nn.functional.normalize(torch.randn(n, 3, generator=gen), dim=1)
+    rw64 = O.render_weights(sd, dtype=torch.float64)
+    with torch.no_grad():
+        rgb_ref = O.render_mlp(x[idx].double(), gref, view[idx].double(), ref64[:, 2:], rw64)
+    rgb = ops.render_forward(rend, x.to(dev), view.to(dev), grad, full[:, 2:].contiguous())
+    assert (rgb.cpu()[idx].double() - rgb_ref).abs().max().item() < TOL_RGB
+    # native backward on a sub-batch against the explicit fp64 chain
+    nb = min(n, 600)
+    xb = x[:nb]
+    g_full = torch.randn(nb, 258, generator=gen) * 1e-3
+    g_grad = torch.randn(nb, 3, generator=gen) * 1e-2
+    vs = [sd[f"implicit_network.lin{l}.weight_v"].double() for l in range(9)]
+    gs = [sd[f"implicit_network.lin{l}.weight_g"].double() for l in range(9)]
+    bs = [sd[f"implicit_network.lin{l}.bias"].double() for l in range(9)]
+    dx_ref, dv_ref, dg_ref, db_ref = S.sdf_value_grad_backward(xb.double(), vs, gs, bs, (4,), 6, g_full.double(), g_grad.double())
+    _, _, save = ops.sdf_forward_train(sdf, xb.to(dev))
+    dx, dw, db = ops.sdf_backward(sdf, xb.to(dev), save, g_full.to(dev), g_grad.to(dev), need_dx=True)
+    assert (dx.cpu().double() - dx_ref).abs().max().item() <= 2e-4 * dx_ref.abs().max().item()
+    dvs, dgs, dbs = ops.weight_grads(sdf, dw, db, [v.float().to(dev) for v in vs], [g_.float().to(dev) for g_ in gs])
+    for l in range(9):
+        for got, ref in ((dvs[l], dv_ref[l]), (dgs[l], dg_ref[l]), (dbs[l], db_ref[l])):
+            assert (got.reshape(ref.shape).cpu().double() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item(), (width, l)
