@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/mvsdf_b200.h"
 #include "internal.h"
@@ -30,6 +31,8 @@ enum RayFlag : uint32_t {
   F_NET = 1u << 6,       // network_object_mask
   F_SECANT = 1u << 7,
   F_MINSDF = 1u << 8,
+  F_SPEC_S = 1u << 9,    // the start / end march has speculative back-off requests pending (trace_backoff_spec_kernel)
+  F_SPEC_E = 1u << 10,
 };
 
 struct RayState {
@@ -71,6 +74,7 @@ struct TraceCtx {
   int* counters;     // [kNumCounters]  request counts per phase; the last four slots are fixed (see kCtr*)
   int* ref_counters; // [kNumCounters]  prefilter: refined samples per 100-sample batch
   int* pf_counts;    // [kNumCounters]  prefilter: per (batch, sample chunk) active rays / points of the chunked screening pass
+  int* spec_counts;  // [kNumCounters]  sphere tracing: size of the speculative back-off request list of every iteration
   int* act_list[2];  // [batch_rays]    rays of the batch that still need their next sample chunk (ping-pong)
   int R, N;
   long long cap;
@@ -167,12 +171,50 @@ __device__ __forceinline__ void collect(const TraceCtx& c, int r) {
   }
 }
 
+// The overshoot back-off loop (ray_tracing.py:173-191) steps a ray that crossed the surface back by 1/2, 1/4, 1/8 ... of its
+// last step until the SDF is non-negative again, at most line_step_iters times.  Every candidate position is known before the
+// first of these evaluations (the step length curr_sdf is fixed), so trace_backoff_spec_kernel queues ALL of a ray's
+// candidates at once and the walk "take candidate k while the value is still negative" is replayed on the results here:
+// identical arithmetic, identical values, one MLP launch per sphere-tracing iteration instead of line_step_iters (each
+// launch, however small, streams the whole network through at least one SM pair).  Evaluations the reference would not have
+// made are not counted: `used` goes into the iteration's E_trace counter.
+__device__ __forceinline__ void resolve_backoff(const TraceCtx& c, int r, uint32_t& fl, int n_k, int count_ctr) {
+  int used = 0;
+  if (fl & F_SPEC_S) {
+    float a = c.s.acc_s[r], v = c.s.next_s[r];
+    const float cur = c.s.cur_s[r];
+    const int first = c.s.slot_s[r];
+    for (int k = 0; k < n_k && v < 0.f; ++k, ++used) {
+      a = __fsub_rn(a, __fmul_rn((1.0f - c.line_step) / (float)(1 << k), cur));
+      v = clampf(c.req_val[first + k], c.clip);
+    }
+    c.s.acc_s[r] = a;
+    c.s.next_s[r] = v;
+    c.s.slot_s[r] = -1;
+  }
+  if (fl & F_SPEC_E) {
+    float a = c.s.acc_e[r], v = c.s.next_e[r];
+    const float cur = c.s.cur_e[r];
+    const int first = c.s.slot_e[r];
+    for (int k = 0; k < n_k && v < 0.f; ++k, ++used) {
+      a = __fadd_rn(a, __fmul_rn((1.0f - c.line_step) / (float)(1 << k), cur));
+      v = clampf(c.req_val[first + k], c.clip);
+    }
+    c.s.acc_e[r] = a;
+    c.s.next_e[r] = v;
+    c.s.slot_e[r] = -1;
+  }
+  fl &= ~(F_SPEC_S | F_SPEC_E);
+  if (used) atomicAdd(c.counters + count_ctr, used);
+}
+
 // top of the while-loop body (ray_tracing.py:139-171); `first`: no end-of-body update yet; `last`: iters == max
-__global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter) {
+__global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter, int n_k, int backoff_ctr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= c.R) return;
   uint32_t fl = c.s.flags[r];
   if (!(fl & F_HIT_SPHERE)) return;
+  if (fl & (F_SPEC_S | F_SPEC_E)) resolve_backoff(c, r, fl, n_k, backoff_ctr);
   collect(c, r);
   float acc_s = c.s.acc_s[r], acc_e = c.s.acc_e[r];
   if (!first) {   // end of the previous body (:193-194)
@@ -202,7 +244,8 @@ __global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter) {
   c.s.flags[r] = fl;
 }
 
-// one pass of the overshoot back-off loop (ray_tracing.py:173-191)
+// one pass of the overshoot back-off loop (ray_tracing.py:173-191), sequential form: used when the request list cannot hold
+// every candidate of every ray at once (2 R line_step_iters entries in the worst case)
 __global__ void trace_backoff_kernel(TraceCtx c, int k, int counter) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= c.R) return;
@@ -222,6 +265,46 @@ __global__ void trace_backoff_kernel(TraceCtx c, int k, int counter) {
     c.s.acc_e[r] = a;
     c.s.slot_e[r] = push_request(c, counter, ray_point(cam, d, a));
   }
+}
+
+// all candidates of the overshoot back-off loop of one sphere-tracing iteration (see resolve_backoff)
+__global__ void trace_backoff_spec_kernel(TraceCtx c, int n_k, int* __restrict__ spec_count) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  uint32_t fl = c.s.flags[r];
+  if (!(fl & F_HIT_SPHERE)) return;
+  collect(c, r);
+  const float* cam = c.cam + 3 * (r / c.N);
+  const float* d = c.s.dir + 3 * (size_t)r;
+  if (c.s.next_s[r] < 0.f) {
+    const int first = atomicAdd(spec_count, n_k);
+    float a = c.s.acc_s[r];
+    const float cur = c.s.cur_s[r];
+    for (int k = 0; k < n_k; ++k) {
+      a = __fsub_rn(a, __fmul_rn((1.0f - c.line_step) / (float)(1 << k), cur));
+      const float3 p = ray_point(cam, d, a);
+      c.req_pts[3 * (size_t)(first + k)] = p.x;
+      c.req_pts[3 * (size_t)(first + k) + 1] = p.y;
+      c.req_pts[3 * (size_t)(first + k) + 2] = p.z;
+    }
+    c.s.slot_s[r] = first;
+    fl |= F_SPEC_S;
+  }
+  if (c.s.next_e[r] < 0.f) {
+    const int first = atomicAdd(spec_count, n_k);
+    float a = c.s.acc_e[r];
+    const float cur = c.s.cur_e[r];
+    for (int k = 0; k < n_k; ++k) {
+      a = __fadd_rn(a, __fmul_rn((1.0f - c.line_step) / (float)(1 << k), cur));
+      const float3 p = ray_point(cam, d, a);
+      c.req_pts[3 * (size_t)(first + k)] = p.x;
+      c.req_pts[3 * (size_t)(first + k) + 1] = p.y;
+      c.req_pts[3 * (size_t)(first + k) + 2] = p.z;
+    }
+    c.s.slot_e[r] = first;
+    fl |= F_SPEC_E;
+  }
+  c.s.flags[r] = fl;
 }
 
 // after the loop: network_object_mask = acc_s < acc_e (:41); unconverged start rays go to the sampler (:44)
@@ -590,7 +673,7 @@ static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  w.off_counters = take(3 * kNumCounters * 4);
+  w.off_counters = take(4 * kNumCounters * 4);
   w.off_cam = take((size_t)B * 3 * 4);
   for (int i = 0; i < 9; ++i) w.off_f[i] = take((size_t)R * 4);       // acc_s acc_e min max next_s next_e cur_s cur_e z
   for (int i = 0; i < 4; ++i) w.off_i[i] = take((size_t)R * 4);       // slot_s slot_e list list_pos
@@ -676,6 +759,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.counters = reinterpret_cast<int*>(ws + w.off_counters);
   c.ref_counters = c.counters + kNumCounters;
   c.pf_counts = c.counters + 2 * kNumCounters;
+  c.spec_counts = c.counters + 3 * kNumCounters;
   for (int i = 0; i < 2; ++i) c.act_list[i] = reinterpret_cast<int*>(ws + w.off_act[i]);
   c.R = (int)R;
   c.N = n_pixels;
@@ -684,7 +768,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.clip = prm->dist_clip;
   c.line_step = prm->line_search_step;
 
-  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 3 * kNumCounters * 4, st), "memset counters");
+  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 4 * kNumCounters * 4, st), "memset counters");
   if (rc) return rc;
   const int grid_r = (int)((R + kBlock - 1) / kBlock);
   int ctr = 0;   // every request phase uses its own counter: no resets, no host round trips
@@ -712,15 +796,29 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   };
   note_launch(); ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr);
   if ((rc = eval(ctr++))) return rc;
+  const int n_k = prm->line_step_iters;
+  // worst case every ray overshoots at both ends: 2 R n_k candidates must fit the request list; MVSDF_SPEC_BACKOFF=0 forces
+  // the sequential form (A/B)
+  static const bool spec_env = !(getenv("MVSDF_SPEC_BACKOFF") && atoi(getenv("MVSDF_SPEC_BACKOFF")) == 0);
+  const bool speculative = spec_env && 2ll * R * n_k <= c.cap;
+  int backoff_ctr = 0;      // E_trace slot of the previous iteration's back-off evaluations (filled by the next trace_top_kernel)
   for (int it = 0; it < prm->sphere_tracing_iters; ++it) {
-    note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr);
+    note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr, n_k, backoff_ctr);
     if ((rc = eval(ctr++))) return rc;
-    for (int k = 0; k < prm->line_step_iters; ++k) {
-      note_launch(); trace_backoff_kernel<<<grid_r, kBlock, 0, st>>>(c, k, ctr);
-      if ((rc = eval(ctr++))) return rc;
+    if (n_k > 0 && speculative) {
+      // the whole back-off loop of this iteration in one launch (resolve_backoff)
+      note_launch(); trace_backoff_spec_kernel<<<grid_r, kBlock, 0, st>>>(c, n_k, c.spec_counts + it);
+      if ((rc = mlp_sdf(net, packed, c.req_pts, 0, c.spec_counts + it, MVSDF_HEAD_SDF_ONLY, c.req_val, nullptr, nullptr, false, st)))
+        return rc;
+      backoff_ctr = ctr++;
+    } else {
+      for (int k = 0; k < n_k; ++k) {
+        note_launch(); trace_backoff_kernel<<<grid_r, kBlock, 0, st>>>(c, k, ctr);
+        if ((rc = eval(ctr++))) return rc;
+      }
     }
   }
-  note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr);
+  note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr, n_k, backoff_ctr);
   const int list_ctr = kCtrSamplerRays;
   note_launch(); trace_finish_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr);
   // sampler in batches of batch_rays rays (worst case: every ray unconverged)
