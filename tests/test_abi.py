@@ -119,3 +119,48 @@ def test_argument_validation_of_the_tracer_and_loss_entry_points(lib):
     assert lib.mvsdf_feat_loss_backward(d, d, d, d, 1, 2, 8, 8, 16, d, d, d, d, d, None) == -1
     assert lib.mvsdf_rgb_l1_partials(d, d, d, 0, d, None) == -1
     assert lib.mvsdf_depth_loss_partials(d, 2, d, 10, d, d, 1, 8, 8, d, d, 0.5, 1.0, 1.0, 1.0, 1.0, d, d, d, None) == -1
+
+
+def test_argument_validation_of_the_round2_entry_points(lib):
+    """Training step, FeatExt, scene-store and counter-budget checks: bad arguments are rejected with a negative status and a
+    message before the device is touched (no GPU needed)."""
+    from mvsdf_b200 import ops
+    P = ctypes.c_void_p
+    d = P(256)
+    sdf = ops.PackedNet("sdf", 256, 8)
+    rend = ops.PackedNet("render", 256, 4, n_freqs=4)
+    # sizes reported by the planning calls are consistent
+    assert lib.mvsdf_train_packed_t_bytes(sdf.handle) > 2_000_000
+    assert lib.mvsdf_train_dw_floats(sdf.handle) >= 256 * 64 + 7 * 256 * 256 + 384 * 256
+    assert lib.mvsdf_train_db_floats(sdf.handle) == 8 * 256 + 384
+    s16, s17 = lib.mvsdf_train_save_bytes(sdf.handle, 16, 1), lib.mvsdf_train_save_bytes(sdf.handle, 17, 1)
+    assert s17 > s16 > 0 and lib.mvsdf_train_save_bytes(sdf.handle, 64, 0) == lib.mvsdf_train_save_bytes(sdf.handle, 16, 1)
+    assert lib.mvsdf_train_workspace_bytes(rend.handle, 1000, 0) > 0
+    # wrong plan kind / null pointers / short buffers
+    assert lib.mvsdf_sdf_forward_train(rend.handle, d, d, 10, 1 << 30, d, d, d, None) == -1 and b"SDF net" in lib.mvsdf_last_error()
+    assert lib.mvsdf_sdf_forward_train(sdf.handle, d, d, 10, 16, d, d, d, None) == -3 and b"save buffer" in lib.mvsdf_last_error()
+    assert lib.mvsdf_sdf_forward_train(sdf.handle, d, d, 10, 1 << 30, None, d, d, None) == -1
+    assert lib.mvsdf_sdf_backward(sdf.handle, d, d, 0, d, d, d, 1 << 30, d, None, d, d, None) == -1 and b"empty" in lib.mvsdf_last_error()
+    assert lib.mvsdf_sdf_backward(rend.handle, d, d, 10, d, d, d, 1 << 30, d, None, d, d, None) == -1
+    assert lib.mvsdf_render_backward(rend.handle, d, 10, d, d, None, None, 1 << 30, d, d, d, d, None, d, d, None) == -1
+    assert lib.mvsdf_render_backward(rend.handle, d, 10, d, d, d, None, 1 << 30, d, d, d, d, d, d, d, None) == -1 and b"view_dirs" in lib.mvsdf_last_error()
+    assert lib.mvsdf_weight_grads(sdf.handle, None, d, None, None, None, None, None, None) == -1
+    assert lib.mvsdf_adam_step(0, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 1, 0.0, d, None, None) == -1
+    assert lib.mvsdf_adam_step(1, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0, 0.0, d, None, None) == -1
+    # FeatExt: 27 convolutions, image sides multiples of 8, workspace
+    assert lib.mvsdf_featext_num_convs() == 27 and lib.mvsdf_featext_packed_floats() > 1_000_000
+    need = lib.mvsdf_featext_workspace_bytes(2, 48, 64)
+    assert need > 2 * 48 * 64 * 3 * 4
+    assert lib.mvsdf_featext_forward(d, d, 2, 50, 64, need, d, None, None, d, None) == -1 and b"multiples of 8" in lib.mvsdf_last_error()
+    assert lib.mvsdf_featext_forward(d, d, 2, 48, 64, need - 64, d, None, None, d, None) == -3
+    assert lib.mvsdf_featext_forward(d, d, 2, 48, 64, need, d, None, None, None, None) == -1
+    # scene-store variant of the feature loss validates like the tensor one
+    assert lib.mvsdf_feat_loss_partials_indexed(d, d, d, d, d, 1, 2, 8, 8, 16, d, d, d, None) == -1 and b"32" in lib.mvsdf_last_error()
+    # the tracer refuses phase counts that would run out of request counters (ADVICE r1), before launching anything
+    net = ops.PackedNet("sdf", 256, 8)
+    prm = lib.TracerParams(1.0, 5e-5, 0.5, 0.5, 8, 64, 100, 8, 0, 0.0)          # 1 + 64 * 9 phases > 251 counters
+    ws_need = lib.mvsdf_trace_workspace_bytes(1024, 1)
+    rc = lib.mvsdf_trace(net.handle, d, d, d, d, None, ctypes.byref(prm), 1, 1024, 0, d, None, ctypes.c_size_t(ws_need), d, d, d, d, d, d, d, None)
+    assert rc == -1 and b"request counters" in lib.mvsdf_last_error()
+    # widths outside the whole-tile family are refused for both nets
+    assert not lib.mvsdf_render_net_create(320, 4, 4, 256) and not lib.mvsdf_render_net_create(64, 4, 4, 256)
