@@ -680,7 +680,8 @@ def run_reference(args):
     res["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": R / value * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": R / value * 1e3, "higher_is_better": True,
+        "scaling": "strong" if (cfg.get("shard_rays") and args.scaling == "strong") else "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['H']}x{cfg['W']} image, {cfg['n_src']} src views, 8x{cfg['width']} SDF MLP + "
                                f"4x{cfg['width']} render MLP, eval-mode forward + feat loss + rgb L1; CPU, bounded sample per step",
