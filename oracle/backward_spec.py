@@ -72,7 +72,7 @@ def sdf_value_grad_backward(x: torch.Tensor, vs: Sequence[torch.Tensor], gs: Seq
     """x [P,3]; vs/gs/bs = weight_v [out,in] / weight_g [out,1] / bias [out] per layer; g_full [P, 2+F]; g_grad [P,3].
     Returns (dx [P,3], [dv_l], [dg_l], [db_l]).  `trace` (optional dict) receives the per-layer intermediates
     H, T (layer inputs), DZ, DS (gradients w.r.t. the pre-activations) and DW (w.r.t. the folded weights) -- what the
-    kernels of csrc/mlp_bwd_kernel.cuh keep in their saved / dumped images (tools/diag_backward.py compares them)."""
+    kernels of csrc/mlp_bwd_kernel.cuh keep in their saved / dumped images (tests/diag/diag_backward.py compares them)."""
     n = len(vs)
     W = [fold(v, g) for v, g in zip(vs, gs)]
     pe, dpe, d2pe = _pe_all(x, n_freqs)

@@ -4,7 +4,7 @@ layer so that a wrong layout / scale / epilogue shows up where it happens.  Test
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from mvsdf_b200 import _lib, ops, synth
