@@ -79,6 +79,61 @@ class SdfEval(torch.autograd.Function):
         return (None, None, dx, *_interleave(dvs, dgs, dbs, needs[1:]))
 
 
+class SurfaceEval(torch.autograd.Function):
+    """(full_s, g_s, x_diff, full_d, n_d) = SurfaceEval.apply(net, x_s, t_s, c_s, d_s, *params) -- everything IDRNetwork.forward
+    evaluates at the surface points in one node (fixed cameras):
+
+      full_s, g_s   ImplicitNetwork(x_s) and its gradient at the traced points x_s = c + t d (:202, :275),
+      x_diff        the implicit-differentiation point  c + (t - (f(x_s; theta) - f_0) / (g_0 . d)) d  (sample_network.py:10-20),
+      full_d, n_d   ImplicitNetwork(x_diff) and its gradient: features and normals of get_rbg_value (:324-338).
+
+    In value x_diff = x_s, so ONE forward pass serves all five outputs.  The backward exploits that the reverse sweep is
+    linear in its upstream gradients and that both evaluations share the saved activations: a dx-only sweep of (G_full_d,
+    G_n_d) gives dL/d x_diff, which enters f(x_s; theta)'s upstream as  -(dL/d x_diff . d) / (g_0 . d); ONE full sweep
+    (with the dW GEMM) of the summed upstreams then yields all parameter gradients -- instead of two full backward passes
+    over the surface set (two autograd nodes), which is what the generic SdfEval path does with trained cameras."""
+
+    @staticmethod
+    def forward(ctx, net: ops.PackedNet, x_s, t_s, c_s, d_s, *params):
+        full, grad, save = ops.sdf_forward_train(net, x_s)
+        ctx.net = net
+        ctx.save = save
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x_s, d_s, grad, *params)
+        x_diff = c_s + t_s * d_s
+        return full, grad, x_diff, full.clone(), grad.clone()
+
+    @staticmethod
+    def backward(ctx, g_full_s, g_g_s, g_xdiff, g_full_d, g_n_d):
+        x_s, d_s, grad0, *params = ctx.saved_tensors
+        net = ctx.net
+        needs = ctx.needs_input_grad[5:]
+        n = x_s.shape[0]
+        if n == 0 or all(g is None for g in (g_full_s, g_g_s, g_xdiff, g_full_d, g_n_d)):
+            return (None, None, None, None, None, *[torch.zeros_like(p) if nd else None for p, nd in zip(params, needs)])
+        dxt = g_xdiff
+        if g_full_d is not None or g_n_d is not None:
+            dx_d, _, _ = ops.sdf_backward(net, x_s, ctx.save, g_full_d, g_n_d, need_dx=True, need_dw=False)
+            dxt = dx_d if dxt is None else dxt + dx_d
+        g_full = None
+        for g in (g_full_s, g_full_d):
+            if g is not None:
+                g_full = g.clone() if g_full is None else g_full + g
+        if dxt is not None:
+            alpha = -(dxt * d_s).sum(-1) / (grad0 * d_s).sum(-1)
+            if g_full is None:
+                g_full = torch.zeros(n, net.feature_size + 2, dtype=torch.float32, device=x_s.device)
+            g_full[:, 0] += alpha
+        g_grad = None
+        for g in (g_g_s, g_n_d):
+            if g is not None:
+                g_grad = g if g_grad is None else g_grad + g
+        _, dw, db = ops.sdf_backward(net, x_s, ctx.save, g_full, g_grad, need_dx=False)
+        vs, gs, _ = _param_lists(params)
+        dvs, dgs, dbs = ops.weight_grads(net, dw, db, vs, gs)
+        return (None, None, None, None, None, *_interleave(dvs, dgs, dbs, needs))
+
+
 class RenderEval(torch.autograd.Function):
     """rgb = RenderEval.apply(net, points, normals, view, feats, *params).  The gradient w.r.t. the view direction is only
     produced when it is asked for (trained camera poses; otherwise the view direction is a constant of the ray)."""

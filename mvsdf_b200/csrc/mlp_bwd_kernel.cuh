@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
         const int fl = a.fwd_layer[0];
         const int kc = a.dz_kc[fl];
         const int kpad = kc * 8;
-        uint8_t* gimg = a.dz + a.dz_off[fl] + (size_t)tile * ((size_t)kc * kBCoreStride);
+        uint8_t* gimg = a.dz ? a.dz + a.dz_off[fl] + (size_t)tile * ((size_t)kc * kBCoreStride) : nullptr;   // nullptr: dx-only sweep
         for (int cidx = t; cidx < kTileN * kpad; cidx += kEpiThreads) {
           const int col = cidx / kpad, k = cidx - col * kpad;
           float v = 0.0f;
@@ -218,9 +218,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
           const uint32_t o = xoff(col, k);
           ptx::st_shared_u16(s_xhi + o, __half_as_ushort(h));
           ptx::st_shared_u16(s_xlo + o, __half_as_ushort(lo));
-          uint8_t* gd = gimg + save_addr(kc, k, col >> 3) + (col & 7) * 2;
-          *reinterpret_cast<__half*>(gd) = h;
-          *reinterpret_cast<__half*>(gd + 256) = lo;
+          if (gimg) {
+            uint8_t* gd = gimg + save_addr(kc, k, col >> 3) + (col & 7) * 2;
+            *reinterpret_cast<__half*>(gd) = h;
+            *reinterpret_cast<__half*>(gd + 256) = lo;
+          }
         }
       }
       ptx::tc_fence_before();
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
                 }
                 if (MODE == 1 && have_h) {
                   const float bsum = o[0] + o[4] + o[8] + o[12];
-                  if (f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum * invS);
+                  if (a.db && f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum * invS);
                 }
               } else {
                 float bsum = 0.0f;
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
                   o[j] = h > 0.0f ? d[j] : 0.0f;                 // ReLU'
                   bsum += o[j];
                 }
-                if (have_h && f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum * invS);
+                if (a.db && have_h && f < a.Lt[l + 1].in_dim) atomicAdd(a.db + a.db_off[fl - 1] + f, bsum * invS);
               }
               if (!have_h) {
 #pragma unroll
@@ -384,13 +386,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_sweep_kernel(const Bwd
         if (!last) {
           // every UMMA of this step has retired: the new operand [dZ_{fl-1} | dS_{fl-1}] overwrites the buffer in place
           const int kc_out = a.dz_kc[fl - 1];
-          uint8_t* gimg = a.dz + a.dz_off[fl - 1] + (size_t)tile * ((size_t)kc_out * kBCoreStride);
+          uint8_t* gimg = a.dz ? a.dz + a.dz_off[fl - 1] + (size_t)tile * ((size_t)kc_out * kBCoreStride) : nullptr;
 #pragma unroll
           for (int m = 0; m < kMaxTiles; ++m) {
             if (m < lp.m_tiles) {
               const int f = m * kTileM + row;
               const uint32_t o0 = xoff(cg * 16, f);
-              uint8_t* gd = f < kc_out * 8 ? gimg + save_addr(kc_out, f, cg * 2) : nullptr;
+              uint8_t* gd = (gimg && f < kc_out * 8) ? gimg + save_addr(kc_out, f, cg * 2) : nullptr;
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 ptx::st_shared_v4(s_xhi + o0 + j * 128, phi[m][4 * j], phi[m][4 * j + 1], phi[m][4 * j + 2], phi[m][4 * j + 3]);

@@ -308,14 +308,16 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
   BwdArgs a;
   memset(&a, 0, sizeof(a));
   dz_offsets(t, n_tiles, kWsHeader, a.dz_off, &dz_total);
-  if ((long long)ws_bytes < dz_total) return fail(MVSDF_ERR_WORKSPACE, "backward workspace too small (%zu < %lld)", ws_bytes, dz_total);
+  const bool with_dw = out_dw != nullptr;       // false: dx-only sweep (no gradient dumps, no dW GEMM, no bias gradients)
+  if ((long long)ws_bytes < (with_dw ? dz_total : kWsHeader))
+    return fail(MVSDF_ERR_WORKSPACE, "backward workspace too small (%zu < %lld)", ws_bytes, with_dw ? dz_total : kWsHeader);
   uint8_t* w8 = static_cast<uint8_t*>(ws);
   float* gscale = reinterpret_cast<float*>(w8);
   unsigned* maxbits = reinterpret_cast<unsigned*>(w8 + 16);
   int rc = check_cuda(cudaMemsetAsync(w8, 0, kWsHeader, st), "memset backward header");
   if (rc) return rc;
-  if ((rc = check_cuda(cudaMemsetAsync(out_dw, 0, (size_t)t.dw_total * 4, st), "memset dW"))) return rc;
-  if ((rc = check_cuda(cudaMemsetAsync(out_db, 0, (size_t)t.db_total * 4, st), "memset db"))) return rc;
+  if (with_dw && (rc = check_cuda(cudaMemsetAsync(out_dw, 0, (size_t)t.dw_total * 4, st), "memset dW"))) return rc;
+  if (with_dw && (rc = check_cuda(cudaMemsetAsync(out_db, 0, (size_t)t.db_total * 4, st), "memset db"))) return rc;
   if (out_dx && (rc = check_cuda(cudaMemsetAsync(out_dx, 0, (size_t)n * 12, st), "memset dx"))) return rc;
   const int sms = sm_count();
   // gradient scale from the upstream magnitudes
@@ -354,8 +356,8 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
   a.g_full = g_full;
   a.g_grad = g_grad;
   a.rgb = rgb;
-  a.dz = w8;
-  a.db = out_db;
+  a.dz = with_dw ? w8 : nullptr;
+  a.db = with_dw ? out_db : nullptr;
   a.dx = out_dx;
   a.d_points = d_points;
   a.d_normals = d_normals;
@@ -366,7 +368,7 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
   {
     const LayerPlan& H = t.fwd[t.n_run - 1];
     const int rows = H.m_tiles * kTileM;
-    if (g_full) {
+    if (g_full && with_dw) {
       note_launch();
       head_db_kernel<<<rows, 256, 0, st>>>(g_full, rgb, n, KIND == NET_SDF ? p.feat_size + 2 : 3, H.row_map, H.out_dim, p.feat_size,
                                           out_db + t.db_off[t.n_run - 1]);
@@ -385,6 +387,7 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
   prof_end_ext(pe, st);
   if ((rc = check_cuda(cudaGetLastError(), "launch mlp_bwd_sweep_kernel"))) return rc;
 
+  if (!with_dw) return MVSDF_OK;
   // dW over the points
   DwArgs d;
   memset(&d, 0, sizeof(d));
@@ -511,7 +514,7 @@ int mvsdf_sdf_backward(const mvsdf_net* net, const void* packed_t, const float* 
                        const float* g_grad, size_t workspace_bytes, void* workspace, float* out_dx, float* out_dw, float* out_db,
                        void* stream) {
   if (!net || net->plan.kind != NET_SDF) return fail(MVSDF_ERR_INVALID, "expected an SDF net plan");
-  if (!packed_t || !x || !save || !workspace || !out_dw || !out_db || n <= 0)
+  if (!packed_t || !x || !save || !workspace || (out_dw && !out_db) || (!out_dw && !out_dx) || n <= 0)
     return fail(MVSDF_ERR_INVALID, "mvsdf_sdf_backward: null argument / empty batch");
   return run_backward<NET_SDF, 1>(net, packed_t, x, n, save, g_full, g_grad, nullptr, workspace_bytes, workspace, out_dx, nullptr,
                                   nullptr, nullptr, out_dw, out_db, static_cast<cudaStream_t>(stream));

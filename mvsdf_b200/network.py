@@ -481,7 +481,7 @@ class B200IDRNetwork(nn.Module):
         """Training forward with an autograd graph: the tracer (no_grad in the reference too, :192-198) is the native
         persistent kernel; the differentiable stages are autograd.Functions whose FORWARD values are the native fused
         kernels and whose backward is documented in mvsdf_b200/autograd.py."""
-        from .autograd import RenderEval, SdfEval
+        from .autograd import RenderEval, SdfEval, SurfaceEval
         conf = self.schedule
         assert train_progress is not None
         uv, pose, intrinsics = ops._f32(input["uv"]), ops._f32(input["pose"]), ops._f32(input["intrinsics"])
@@ -533,17 +533,23 @@ class B200IDRNetwork(nn.Module):
             extra_pts = torch.cat([extra_pts, ds_on, ds_jit], dim=0).contiguous()
 
         shared = {}     # the surface set is evaluated ONCE (the reference does it three times: :202, :325, :326)
-        full_s, g_s = SdfEval.apply(sdf_net, shared, x_s, *sdf_p)                # :202 restricted to the surface rays, :275
+        fused = pose_param is None
+        if fused:
+            # fixed cameras: one node for everything evaluated at the surface points (one forward, one dx-only + one full sweep)
+            full_s, g_s, x_diff, full_d, n_d = SurfaceEval.apply(sdf_net, x_s, t_s, c_s, d_s, *sdf_p)
+        else:
+            full_s, g_s = SdfEval.apply(sdf_net, shared, x_s, *sdf_p)            # :202 restricted to the surface rays, :275
         full_e, g_e = SdfEval.apply(sdf_net, None, extra_pts, *sdf_p)            # :256, :275
         f_s = full_s[:, :1]
         eik_pts = torch.cat([x_s, extra_pts], dim=0)
         keep = object_mask_true[idx]
         # implicit differentiation (model/sample_network.py:10-20)
-        dot = (g_s.detach() * d_s).sum(-1, keepdim=True)
-        x_diff = c_s + (t_s - (f_s - f_s.detach()) / dot) * d_s
-        # get_rbg_value (:324-338)
-        # x_diff equals x_s in value (f_s - f_s.detach() = 0): same forward results, own node in the autograd graph
-        full_d, n_d = SdfEval.apply(sdf_net, shared, x_diff, *sdf_p)
+        if not fused:
+            dot = (g_s.detach() * d_s).sum(-1, keepdim=True)
+            x_diff = c_s + (t_s - (f_s - f_s.detach()) / dot) * d_s
+            # get_rbg_value (:324-338)
+            # x_diff equals x_s in value (f_s - f_s.detach() = 0): same forward results, own node in the autograd graph
+            full_d, n_d = SdfEval.apply(sdf_net, shared, x_diff, *sdf_p)
         feats = full_d[:, 2:]
         p_in, n_in, v_in = x_diff, n_d, -d_s
         if train_progress < conf.phase[0] or conf.disable_rgb_grad:

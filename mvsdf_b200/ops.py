@@ -180,17 +180,18 @@ def sdf_forward_train(net: PackedNet, x: torch.Tensor):
     return full, grad, save
 
 
-def sdf_backward(net: PackedNet, x: torch.Tensor, save: torch.Tensor, g_full, g_grad, need_dx: bool):
-    """Reverse sweep + dW GEMM of the SDF net: returns (dx [n,3] or None, dw [plan floats], db [plan floats])."""
+def sdf_backward(net: PackedNet, x: torch.Tensor, save: torch.Tensor, g_full, g_grad, need_dx: bool, need_dw: bool = True):
+    """Reverse sweep + dW GEMM of the SDF net: returns (dx [n,3] or None, dw [plan floats], db [plan floats]);
+    need_dw=False: dx-only sweep (dw = db = None)."""
     L = _lib.lib()
     x = _f32(x)
     n = x.shape[0]
     dev = x.device
     net.pack_t()
-    dw = torch.empty(L.mvsdf_train_dw_floats(net.handle), dtype=torch.float32, device=dev)
-    db = torch.empty(L.mvsdf_train_db_floats(net.handle), dtype=torch.float32, device=dev)
+    dw = torch.empty(L.mvsdf_train_dw_floats(net.handle), dtype=torch.float32, device=dev) if need_dw else None
+    db = torch.empty(L.mvsdf_train_db_floats(net.handle), dtype=torch.float32, device=dev) if need_dw else None
     dx = torch.empty(n, 3, dtype=torch.float32, device=dev) if need_dx else None
-    ws_bytes = L.mvsdf_train_workspace_bytes(net.handle, n, 1)
+    ws_bytes = L.mvsdf_train_workspace_bytes(net.handle, n, 1) if need_dw else 256
     ws = _scratch("sdf_bwd", ws_bytes, dev)
     g_full = None if g_full is None else _f32(g_full)
     g_grad = None if g_grad is None else _f32(g_grad)
