@@ -468,14 +468,29 @@ class B200IDRNetwork(nn.Module):
         finally:
             self.prefilter_tau = 2.0 * tau if 2.0 * tau <= PREFILTER_TAU_MAX else 0.0
 
-    def _phase0(self, train_progress) -> bool:
+    _SETS = ("rt_surf", "eik", "dsurf_on", "dsurf_jitter")
+
+    def _schedule_flags(self, train_progress):
+        """The eight point-set switches of model/conf.py:4-14: which of (ray-traced surface points, uniform eikonal samples,
+        depth-surface samples, jittered depth-surface samples) enter eikonal_output / eikonal_points_hom (d_use_*,
+        implicit_differentiable_renderer.py:259-270) and grad_theta (eik_use_*, :277-286)."""
         conf = self.schedule
-        flags = [conf.d_use_dsurf_on(train_progress), conf.d_use_dsurf_jitter(train_progress),
-                 conf.eik_use_dsurf_on(train_progress), conf.eik_use_dsurf_jitter(train_progress)]
-        if any(flags) and not all(flags):
-            raise NotImplementedError("schedules that enable only some of d_use_dsurf_* / eik_use_dsurf_* "
-                                      "(model/conf.py ships them switched together)")
-        return any(flags)
+        d = [bool(getattr(conf, "d_use_" + n)(train_progress)) for n in self._SETS]
+        e = [bool(getattr(conf, "eik_use_" + n)(train_progress)) for n in self._SETS]
+        return d, e
+
+    def _phase0(self, train_progress) -> bool:
+        """Depth-surface samples are drawn when any of the four dsurf switches is on (:226-227)."""
+        d, e = self._schedule_flags(train_progress)
+        return any(d[2:] + e[2:])
+
+    @staticmethod
+    def _select_sets(tensor, n_hit, n_eik, n_ds, flags):
+        """Slices of a [n_hit + n_eik + 2 n_ds, ...] tensor (sets in the reference's order) kept by the switches."""
+        bounds = [(0, n_hit), (n_hit, n_hit + n_eik), (n_hit + n_eik, n_hit + n_eik + n_ds), (n_hit + n_eik + n_ds, n_hit + n_eik + 2 * n_ds)]
+        if all(flags):
+            return tensor
+        return torch.cat([tensor[a:b] for (a, b), on in zip(bounds, flags) if on], dim=0)
 
     def _forward_autograd(self, input, train_progress, steps01, eik_points, dsurf_rand):
         """Training forward with an autograd graph: the tracer (no_grad in the reference too, :192-198) is the native
@@ -541,7 +556,9 @@ class B200IDRNetwork(nn.Module):
             full_s, g_s = SdfEval.apply(sdf_net, shared, x_s, *sdf_p)            # :202 restricted to the surface rays, :275
         full_e, g_e = SdfEval.apply(sdf_net, None, extra_pts, *sdf_p)            # :256, :275
         f_s = full_s[:, :1]
-        eik_pts = torch.cat([x_s, extra_pts], dim=0)
+        d_flags, e_flags = self._schedule_flags(train_progress)
+        n_ds = (extra_pts.shape[0] - n_eik) // 2
+        eik_sel = self._select_sets(torch.cat([x_s, extra_pts], dim=0), M, n_eik, n_ds, d_flags)
         keep = object_mask_true[idx]
         # implicit differentiation (model/sample_network.py:10-20)
         if not fused:
@@ -568,9 +585,9 @@ class B200IDRNetwork(nn.Module):
             "network_object_mask": network_object_mask,
             "object_mask": object_mask,
             "object_mask_true": object_mask_true,
-            "grad_theta": torch.cat([g_s, g_e], dim=0),
-            "eikonal_points_hom": torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1),
-            "eikonal_output": torch.cat([f_s, full_e[:, :1]], dim=0).view(1, -1),
+            "grad_theta": self._select_sets(torch.cat([g_s, g_e], dim=0), M, n_eik, n_ds, e_flags),
+            "eikonal_points_hom": torch.cat([eik_sel, torch.ones_like(eik_sel[:, -1:])], dim=-1).view(1, -1, 4, 1),
+            "eikonal_output": self._select_sets(torch.cat([f_s, full_e[:, :1]], dim=0), M, n_eik, n_ds, d_flags).view(1, -1),
             "surf_indicator_output": torch.cat([full_s[:, 1][keep], full_e[:n_eik, 1]], dim=0),
             "hit_offsets": hit_offsets,
             "surface_normals": n_d,
@@ -638,12 +655,14 @@ class B200IDRNetwork(nn.Module):
         if training:
             extra, g_extra = raw["extra"], raw["g_extra"]
             f_s = surf_head[:M, 0:1]
-            eik_pts = torch.cat([diff_surf_pts, extra_pts], dim=0)
-            output["eikonal_output"] = torch.cat([f_s, extra[:, :1]], dim=0).view(1, -1)
+            d_flags, e_flags = self._schedule_flags(train_progress)
+            n_ds = (extra_pts.shape[0] - n_eik) // 2
+            eik_pts = self._select_sets(torch.cat([diff_surf_pts, extra_pts], dim=0), M, n_eik, n_ds, d_flags)
+            output["eikonal_output"] = self._select_sets(torch.cat([f_s, extra[:, :1]], dim=0), M, n_eik, n_ds, d_flags).view(1, -1)
             output["eikonal_points_hom"] = torch.cat([eik_pts, torch.ones_like(eik_pts[:, -1:])], dim=-1).view(1, -1, 4, 1)
             keep = object_mask_true[hit_index[:M].long()]
             output["surf_indicator_output"] = torch.cat([surf_head[:M, 1][keep], extra[:n_eik, 1]], dim=0)
-            output["grad_theta"] = torch.cat([normals[:M], g_extra], dim=0)
+            output["grad_theta"] = self._select_sets(torch.cat([normals[:M], g_extra], dim=0), M, n_eik, n_ds, e_flags)
         return output
 
     def _enqueue_native(self, training, uv, pose, intrinsics, obj_u8, steps_dev, extra_pts):

@@ -237,3 +237,51 @@ def test_shard_invariance_of_loss_partials():
         acc_feat += l2.last_partials["feat"]
     assert torch.allclose(acc_rgb, p_rgb, rtol=1e-12, atol=1e-12)
     assert torch.allclose(acc_feat, p_feat, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("with_grad", [False, True])
+def test_custom_schedule_switches_vs_oracle(with_grad):
+    """A schedule module other than the shipped one (the reference's IDR_USE_ENV=1 + IDR_CONF=<module> override, :15-17) with the
+    eight point-set switches of model/conf.py:4-14 in a mixed combination: eikonal_output / eikonal_points_hom / grad_theta
+    are assembled from the selected sets only (:259-286), on the native and on the autograd path; the oracle's restatement of
+    the switches is pinned to the live reference in tests/test_oracle.py."""
+    import types
+    import numpy as np
+    from mvsdf_b200 import conf as shipped
+    from mvsdf_b200.network import B200IDRNetwork, default_conf
+    dev = torch.device("cuda:0")
+    sd = preset_state_dict("w256")
+    tp = 0.3
+    sched = types.SimpleNamespace(**{k: getattr(shipped, k) for k in dir(shipped) if not k.startswith("_")})
+    sched.d_use_eik = lambda t: False
+    sched.d_use_dsurf_on = lambda t: True
+    sched.eik_use_rt_surf = lambda t: False
+    sched.eik_use_dsurf_jitter = lambda t: True
+    scene = synth_scene = __import__("mvsdf_b200.synth", fromlist=["x"]).make_scene(48, 48, n_images=2, n_src=1, n_rays=128, seed=9)
+    g = torch.Generator().manual_seed(5)
+    steps = torch.rand(100, generator=g)
+    eik = torch.rand(128, 3, generator=g) * 2 - 1
+    ds = O.depth_surface_points(scene["depths"], scene["depth_cams"], scene["center"][:1], scene["size"][:1])
+    torch.manual_seed(11)
+    np.random.seed(11)
+    _, _, rnd = O.depth_surface_samples(ds, 128, 1.0)
+    with torch.no_grad():
+        ref = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), scene, tp, True, steps01=steps, eik_points=eik, dsurf_rand=rnd,
+                            schedule=sched)
+    model = B200IDRNetwork(default_conf(256), schedule=sched).to(dev)
+    model.load_state_dict(sd)
+    model.train()
+    keys = ["uv", "pose", "intrinsics", "object_mask", "depths", "depth_cams", "center", "size"]
+    rnd_dev = {k: (v.to(dev) if k == "jitter01" else v.cpu().numpy()) for k, v in rnd.items()}
+    ctx = torch.enable_grad() if with_grad else torch.no_grad()
+    with ctx:
+        out = model(_to(scene, keys, dev), tp, steps01=steps, eik_points=eik, dsurf_rand=rnd_dev)
+    assert bool(out["rgb_values"].requires_grad) == with_grad
+    if int((out["network_object_mask"].cpu() != ref["network_object_mask"]).sum()) != 0:
+        pytest.skip("a discrete tracer decision flipped on this input")
+    n_hit = int(ref["network_object_mask"].sum())
+    assert out["eikonal_output"].shape == ref["eikonal_output"].shape == (1, n_hit + 128)
+    assert out["grad_theta"].shape == ref["grad_theta"].shape == (256, 3)
+    gate("eikonal_output_abs_max", (out["eikonal_output"].detach().cpu() - ref["eikonal_output"]).abs().max().item(), G_SDF_MAX)
+    gate("eikonal_points_abs_max", (out["eikonal_points_hom"].detach().cpu() - ref["eikonal_points_hom"]).abs().max().item(), G_SURF_PTS)
+    gate("grad_theta_abs_max", (out["grad_theta"].detach().cpu() - ref["grad_theta"]).abs().max().item(), G_GRAD_THETA)

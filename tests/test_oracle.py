@@ -247,3 +247,46 @@ def test_live_reference_pose_gradients_match_oracle():
     (losses["rgb_loss"] + losses["feat_loss"] + losses["eikonal_loss"]).backward()
     assert p_ref.grad is not None and float(p_ref.grad.abs().max()) > 0
     assert torch.allclose(p_o.grad, p_ref.grad, rtol=2e-3, atol=1e-6 * float(p_ref.grad.abs().max())), (p_o.grad, p_ref.grad)
+
+
+def test_schedule_switches_match_live_reference():
+    """model/conf.py's eight point-set switches (d_use_* / eik_use_*, implicit_differentiable_renderer.py:259-286) in a
+    combination the shipped schedule never produces: the oracle's restatement against the reference with its conf module
+    patched (the reference's own override mechanism is IDR_USE_ENV=1 + IDR_CONF=<module>, :15-17)."""
+    import types
+    import numpy as np
+    ref = ref_shim.load()
+    from mvsdf_b200 import conf as shipped, synth
+    sd = synth.make_state_dict(width=64, seed=5, perturb=0.05, pe_noise=0.003, bias=0.6)
+    model = ref.idr.IDRNetwork(ref_shim.DictConf(ref_shim.model_conf(64)))
+    model.load_state_dict(sd)
+    scene = synth.make_scene(32, 32, n_images=2, n_src=1, n_rays=96, seed=9)
+    tp = 0.3
+    override = dict(d_use_eik=lambda t: False, d_use_dsurf_on=lambda t: True, eik_use_rt_surf=lambda t: False,
+                    eik_use_dsurf_jitter=lambda t: True)
+    sched = types.SimpleNamespace(**{k: getattr(shipped, k) for k in dir(shipped) if not k.startswith("_")})
+    for k, v in override.items():
+        setattr(sched, k, v)
+    saved = {k: getattr(ref.idr.conf, k) for k in override}
+    model.train()
+    try:
+        for k, v in override.items():
+            setattr(ref.idr.conf, k, v)
+        torch.manual_seed(7)
+        np.random.seed(7)
+        with ref_shim.quiet():
+            r = model({k: scene[k].clone() for k in ["uv", "pose", "intrinsics", "object_mask", "depths", "depth_cams", "center", "size"]}, tp)
+    finally:
+        for k, v in saved.items():
+            setattr(ref.idr.conf, k, v)
+    torch.manual_seed(7)
+    np.random.seed(7)
+    o = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), scene, tp, True, schedule=sched)
+    assert torch.equal(o["network_object_mask"], r["network_object_mask"])
+    for k in ("eikonal_output", "eikonal_points_hom", "grad_theta", "surf_indicator_output"):
+        assert o[k].shape == r[k].shape, (k, o[k].shape, r[k].shape)
+        assert torch.allclose(o[k], r[k], rtol=1e-4, atol=1e-5), k
+    n_hit = int((r["network_object_mask"] & r["object_mask"]).sum())
+    n_eik = 96
+    assert r["eikonal_output"].shape[1] == n_hit + n_eik                   # rt-surface + dsurf-on
+    assert r["grad_theta"].shape[0] == n_eik + n_eik                      # eikonal samples + dsurf-jitter
