@@ -556,9 +556,10 @@ def torch_cuda_port_train_sample(cfg, scene, sd, dev, tp, steps01, eik):
             return float(total)
 
         one()
+        one()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        n_it = 2
+        n_it = 3
         for _ in range(n_it):
             one()
         torch.cuda.synchronize(dev)
@@ -566,7 +567,7 @@ def torch_cuda_port_train_sample(cfg, scene, sd, dev, tp, steps01, eik):
         res["skip_min_sdf" if skip else "with_min_sdf"] = {"rays_per_s": R / dt, "ms_per_step": dt * 1e3}
     return {"value": res["with_min_sdf"]["rays_per_s"], "unit": "rays/s", "device": torch.cuda.get_device_name(dev), **res,
             "sample": f"{R} rays ({B} x {N}), full training step (forward + 5 losses + autograd backward + clip + Adam), oracle port on "
-                      "cuda:0 (eager PyTorch fp32, TF32 off), 2 timed steps after 1 warm-up"}
+                      "cuda:0 (eager PyTorch fp32, TF32 off), 3 timed steps after 2 warm-ups"}
 
 
 def cpu_reference_sample(cfg, scene, sd, budget_s=20.0, threads=None):
