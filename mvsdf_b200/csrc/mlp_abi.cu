@@ -234,7 +234,10 @@ static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, b
   const size_t smem = mlp_smem_bytes(p.k_cores_max);
   // the screening-precision instantiation exists for the plain SDF evaluation only (the tracer's sampler prefilter)
   constexpr bool kCanLp = KIND == NET_SDF && MODE == 0 && VER == 2;
-  auto kern = (kCanLp && a.lp) ? mlp_pair2_kernel<KIND, MODE, kCanLp ? 1 : 0> : mlp_pair2_kernel<KIND, MODE, 0>;
+  // the saving instantiation exists for the two training forwards: SDF value+gradient and the rendering net
+  constexpr bool kCanSave = (KIND == NET_SDF && MODE == 1) || (KIND == NET_RENDER && MODE == 0);
+  auto kern = (kCanLp && a.lp) ? mlp_pair2_kernel<KIND, MODE, kCanLp ? 1 : 0>
+                               : ((kCanSave && a.save) ? mlp_pair2_kernel<KIND, MODE, 0, kCanSave ? 1 : 0> : mlp_pair2_kernel<KIND, MODE, 0>);
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "cudaFuncSetAttribute(mlp_pair_kernel)");
   if (rc) return rc;
@@ -260,8 +263,11 @@ static int launch_mlp(const NetPlan& p, MlpArgs& a, int64_t n, const int32_t* n_
   const long long tiles = (n + per_tile - 1) / per_tile;
   if (n_dev == nullptr && tiles == 0) return MVSDF_OK;
   // small host-known batches cannot fill clusters: fall back to single-CTA scheduling (same kernel, CL = 1)
-  if (a.save) return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, false, st);      // training forward: the kernel that saves
   const bool small = n_dev == nullptr && tiles < 2 * sm_count();
+  // training forward (saves the layer inputs): single-CTA kernel for small batches, the CTA-pair kernel otherwise
+  constexpr bool kPairSaves = (KIND == NET_SDF && MODE == 1) || (KIND == NET_RENDER && MODE == 0);
+  static const int pair_save = env_int("MVSDF_PAIR_SAVE", 1);
+  if (a.save && (small || !kPairSaves || !pair_save)) return launch_mlp_cl<KIND, MODE, 1>(p, a, tiles, false, st);
   // 1 = split-K pipelined CTA-pair kernel (default), 0 = single-CTA kernel (A/B runs)
   static const int pair = env_int("MVSDF_PAIR", 1);
   if (pair && !small) return launch_mlp_pair<KIND, MODE, 2>(p, a, (tiles + 1) / 2, n_dev != nullptr, st);

@@ -61,7 +61,9 @@ __device__ __forceinline__ void p2_part(const LayerPlan& lp, int part, int& mp, 
 // per K step instead of three N=128 ones (2/3 of the tensor work for twice the points), the hi half of each weight
 // stage only.  Used by the tracer to decide which of the 100 samples per ray need the exact evaluation at all
 // (csrc/tracer.cu, prefilter); never for an output.
-template <int KIND, int MODE, int LP = 0>
+// SAVE = 1 (training forward): the operand of every layer is also written to global memory in the K-sliced layout of
+// mlp_kernel.cuh (save_addr) for the native backward; a 128-column pair tile g is the 64-column tiles 2g (CTA 0) and 2g + 1.
+template <int KIND, int MODE, int LP = 0, int SAVE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_pair2_kernel(const MlpArgs a) {
   // K chunks per weight-ring stage.  LP: two hi tiles (K = 64) per stage -- at one N=256 UMMA per K step a 32-wide
   // stage is 256 tensor cycles, less than the issuer thread's per-stage latency (~350 cycles)
@@ -365,6 +367,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
           const uint32_t o = xoff(col, k);
           if (LP) ptx::st_shared_u16(s_pehi + o, __half_as_ushort(__float2half_rn(v * kActScale)));
           else store_split(s_pehi + o, s_pelo + o, v * kActScale);
+          if (SAVE) {
+            const __half h = __float2half_rn(v * kActScale);
+            const __half lo = __float2half_rn(v * kActScale - __half2float(h));
+            uint8_t* gsv = a.save + a.save_off[0] + (size_t)(2 * g + crank) * (kPeCores * kBCoreStride) + save_addr(kPeCores, k, col >> 3) +
+                           (col & 7) * 2;
+            *reinterpret_cast<__half*>(gsv) = h;
+            *reinterpret_cast<__half*>(gsv + 256) = lo;
+          }
         }
       } else {
         if (t < kTileN) {
@@ -400,6 +410,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
           }
           const uint32_t o = xoff(col, k);
           store_split(s_xhi + o, s_xlo + o, v * kActScale);
+          if (SAVE) {
+            const int kc0 = kpad >> 3;
+            const __half h = __float2half_rn(v * kActScale);
+            const __half lo = __float2half_rn(v * kActScale - __half2float(h));
+            uint8_t* gsv = a.save + a.save_off[0] + (size_t)(2 * g + crank) * ((size_t)kc0 * kBCoreStride) + save_addr(kc0, k, col >> 3) +
+                           (col & 7) * 2;
+            *reinterpret_cast<__half*>(gsv) = h;
+            *reinterpret_cast<__half*>(gsv + 256) = lo;
+          }
         }
       }
       ptx::tc_fence_before();
@@ -512,6 +531,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                     pack_split_fh(d1 * ts, d2 * ts, phi[2 * gq + 1], plo[2 * gq + 1]);
                   }
                 }
+                if (SAVE && write) {
+                  const int kc_next = a.L[l + 1].k_chunks * (kChunkK / 8);
+                  if (f < kc_next * 8) {
+                    uint8_t* gsv = a.save + a.save_off[l + 1] + (size_t)(2 * g + dest_h) * ((size_t)kc_next * kBCoreStride) +
+                                   save_addr(kc_next, f, cg * 2);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      *reinterpret_cast<uint4*>(gsv + j * 128) = make_uint4(phi[4 * j], phi[4 * j + 1], phi[4 * j + 2], phi[4 * j + 3]);
+                      *reinterpret_cast<uint4*>(gsv + 256 + j * 128) = make_uint4(plo[4 * j], plo[4 * j + 1], plo[4 * j + 2], plo[4 * j + 3]);
+                    }
+                  }
+                }
                 // every UMMA that reads X[mp] of the CURRENT layer retired before D_mp was committed: write in place
                 if (write) {
                   if (hcol == 1) {
@@ -580,6 +611,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
                   const int kd = a.skip_rows_begin + k;
                   const uint4 pv = ptx::ld_shared_v4(s_pehi + (uint32_t)((k >> 3) * kBCoreStride + (k & 7) * 16 + blk * 128));
                   ptx::st_shared_v4(s_xhi + (uint32_t)((kd >> 3) * kBCoreStride + (kd & 7) * 16 + blk * 128), pv.x, pv.y, pv.z, pv.w);
+                  if (SAVE) {      // blocks 0-7: hi parts of column blocks 0-7, blocks 8-15: their lo parts
+                    const int kc_next = a.L[l + 1].k_chunks * (kChunkK / 8);
+                    uint8_t* gsv = a.save + a.save_off[l + 1] + (size_t)(2 * g + crank) * ((size_t)kc_next * kBCoreStride) +
+                                   save_addr(kc_next, kd, blk & 7) + (blk >> 3) * 256;
+                    *reinterpret_cast<uint4*>(gsv) = pv;
+                  }
                 }
               }
               // my rows of X'[mp] for my own columns are written (the peer's rows arrive as st.async bytes on the

@@ -274,7 +274,11 @@ static long long tiles_for(long long n, int with_grad) {
   return (n + per - 1) / per;
 }
 
+// buffers are laid out for an EVEN number of 64-column tiles: the CTA-pair forward writes whole 128-column pair tiles
+static long long alloc_tiles(long long n_tiles) { return (n_tiles + 1) / 2 * 2; }
+
 static void save_offsets(const TrainPlan& t, long long n_tiles, long long* off, long long* total) {
+  n_tiles = alloc_tiles(n_tiles);
   long long o = 0;
   for (int l = 0; l < t.n_run; ++l) {
     off[l] = o;
@@ -285,6 +289,7 @@ static void save_offsets(const TrainPlan& t, long long n_tiles, long long* off, 
 }
 
 static void dz_offsets(const TrainPlan& t, long long n_tiles, long long base, long long* off, long long* total) {
+  n_tiles = alloc_tiles(n_tiles);
   long long o = base;
   for (int l = 0; l < t.n_run; ++l) {
     off[l] = o;

@@ -133,8 +133,9 @@ def test_argument_validation_of_the_round2_entry_points(lib):
     assert lib.mvsdf_train_packed_t_bytes(sdf.handle) > 2_000_000
     assert lib.mvsdf_train_dw_floats(sdf.handle) >= 256 * 64 + 7 * 256 * 256 + 384 * 256
     assert lib.mvsdf_train_db_floats(sdf.handle) == 8 * 256 + 384
-    s16, s17 = lib.mvsdf_train_save_bytes(sdf.handle, 16, 1), lib.mvsdf_train_save_bytes(sdf.handle, 17, 1)
-    assert s17 > s16 > 0 and lib.mvsdf_train_save_bytes(sdf.handle, 64, 0) == lib.mvsdf_train_save_bytes(sdf.handle, 16, 1)
+    # 16 points x 4 columns = one 64-column tile; buffers hold an even number of tiles (the CTA-pair forward writes pair tiles)
+    s16, s33 = lib.mvsdf_train_save_bytes(sdf.handle, 16, 1), lib.mvsdf_train_save_bytes(sdf.handle, 33, 1)
+    assert s33 > s16 > 0 and lib.mvsdf_train_save_bytes(sdf.handle, 64, 0) == s16 == lib.mvsdf_train_save_bytes(sdf.handle, 32, 1)
     assert lib.mvsdf_train_workspace_bytes(rend.handle, 1000, 0) > 0
     # wrong plan kind / null pointers / short buffers
     assert lib.mvsdf_sdf_forward_train(rend.handle, d, d, 10, 1 << 30, d, d, d, None) == -1 and b"SDF net" in lib.mvsdf_last_error()
