@@ -39,12 +39,13 @@ def main(width=256, n=300, seed=0):
     full0, grad0 = ops.sdf_value_grad(net, x.to(dev), ops.HEAD_FULL)
     print("forward_train vs value_grad: full", float((full - full0).abs().max()), "grad", float((grad - grad0).abs().max()))
     n_tiles = (n + 15) // 16
+    n_alloc = (n_tiles + 1) // 2 * 2          # buffers hold an even number of tiles (train_abi.cu alloc_tiles)
     # saved layer inputs
     kcs = [8] + [width // 8] * 8
     off = 0
     for l in range(9):
         img = save[off: off + n_tiles * kcs[l] * 2048]
-        off += n_tiles * kcs[l] * 2048
+        off += n_alloc * kcs[l] * 2048
         dec = decode(img, kcs[l], n_tiles, 64.0).cpu()[: n * 4]                        # [n*4, feat]
         Hl, Tl = tr["H"][l], tr["T"][l]                                                  # [n, feat], [n, feat, 3]
         ref = torch.cat([Hl.unsqueeze(1), Tl.permute(0, 2, 1)], dim=1).reshape(n * 4, -1)   # column = pt*4 + j
@@ -67,7 +68,7 @@ def main(width=256, n=300, seed=0):
     for l in range(9):
         kc = m_tiles[l] * 16
         img = ws[off: off + n_tiles * kc * 2048]
-        off += n_tiles * kc * 2048
+        off += n_alloc * kc * 2048
         dec = decode(img, kc, n_tiles, Sg).cpu()[: n * 4]
         dz, ds = tr["DZ"][l], tr["DS"][l]                                               # [n, out], [n, out, 3]
         ref = torch.cat([dz.unsqueeze(1), ds.permute(0, 2, 1)], dim=1).reshape(n * 4, -1)
