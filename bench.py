@@ -509,7 +509,7 @@ def run_train(args):
         "e2e": {"value": R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 + 4 * 7},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "mlp_bwd_sweep_kernel + mlp_bwd_dw_kernel (reverse sweep and dW GEMM of both MLPs)",
+        "roofline": {"bound": "tensor", "kernel": "mlp_bwd_sweep_pair_kernel + mlp_bwd_dw_kernel (reverse sweep and dW GEMM of both MLPs)",
                      "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
                      "peak_source": peaks["source"] + " bf16_tflops_sustained",

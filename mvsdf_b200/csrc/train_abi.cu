@@ -8,11 +8,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mvsdf_b200.h"
 #include "internal.h"
 #include "mlp_bwd_kernel.cuh"
+#include "mlp_bwd_pair_kernel.cuh"
 
 namespace mvsdf {
 
@@ -298,7 +300,10 @@ static void dz_offsets(const TrainPlan& t, long long n_tiles, long long base, lo
   *total = o;
 }
 
-constexpr long long kWsHeader = 256;       // gscale[2] floats at 0, max bits at 16
+constexpr long long kWsScale = 256;        // gscale[2] floats at 0, max bits at 16
+// then the CTA-pair sweep's scratch for the gradient of the skip-connection PE rows (20 KiB per pair, up to 128 pairs)
+constexpr long long kWsStash = 128 * (long long)kBwdStashBytesPerPair;
+constexpr long long kWsHeader = kWsScale + kWsStash;
 
 template <int KIND, int MODE>
 static int run_backward(const mvsdf_net* net, const void* packed_t, const float* x, long long n, const void* save, const float* g_full,
@@ -319,7 +324,7 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
   uint8_t* w8 = static_cast<uint8_t*>(ws);
   float* gscale = reinterpret_cast<float*>(w8);
   unsigned* maxbits = reinterpret_cast<unsigned*>(w8 + 16);
-  int rc = check_cuda(cudaMemsetAsync(w8, 0, kWsHeader, st), "memset backward header");
+  int rc = check_cuda(cudaMemsetAsync(w8, 0, kWsScale, st), "memset backward header");
   if (rc) return rc;
   if (with_dw && (rc = check_cuda(cudaMemsetAsync(out_dw, 0, (size_t)t.dw_total * 4, st), "memset dW"))) return rc;
   if (with_dw && (rc = check_cuda(cudaMemsetAsync(out_db, 0, (size_t)t.db_total * 4, st), "memset db"))) return rc;
@@ -381,16 +386,32 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
   }
 
   const size_t smem = mlp_smem_bytes(t.k_cores_max);
-  auto kern = mlp_bwd_sweep_kernel<KIND, MODE>;
-  if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute(mlp_bwd_sweep_kernel)")))
-    return rc;
-  const int grid = (int)std::min<long long>(n_tiles, sms);
-  note_launch();
-  void* pe = prof_begin_ext(5, st);
-  kern<<<grid, kMlpThreads, smem, st>>>(a);
-  prof_end_ext(pe, st);
-  if ((rc = check_cuda(cudaGetLastError(), "launch mlp_bwd_sweep_kernel"))) return rc;
+  // batches that fill every SM twice run the CTA-pair sweep (half the weight stream per SM); MVSDF_PAIR_SWEEP=0 keeps the single-CTA one
+  static const bool pair_env = [] { const char* e = getenv("MVSDF_PAIR_SWEEP"); return !(e && e[0] == '0'); }();
+  const int max_pairs = std::min(sms / 2, 128);
+  if (pair_env && n_tiles >= 2LL * sms) {
+    auto kern = mlp_bwd_sweep_pair_kernel<KIND, MODE>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "cudaFuncSetAttribute(mlp_bwd_sweep_pair_kernel)")))
+      return rc;
+    const int n_pairs = (int)std::min<long long>((n_tiles + 1) / 2, max_pairs);
+    note_launch();
+    void* pe = prof_begin_ext(5, st);
+    kern<<<2 * n_pairs, kP2Threads, smem, st>>>(a, reinterpret_cast<float*>(w8 + kWsScale));
+    prof_end_ext(pe, st);
+    if ((rc = check_cuda(cudaGetLastError(), "launch mlp_bwd_sweep_pair_kernel"))) return rc;
+  } else {
+    auto kern = mlp_bwd_sweep_kernel<KIND, MODE>;
+    if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "cudaFuncSetAttribute(mlp_bwd_sweep_kernel)")))
+      return rc;
+    const int grid = (int)std::min<long long>(n_tiles, sms);
+    note_launch();
+    void* pe = prof_begin_ext(5, st);
+    kern<<<grid, kMlpThreads, smem, st>>>(a);
+    prof_end_ext(pe, st);
+    if ((rc = check_cuda(cudaGetLastError(), "launch mlp_bwd_sweep_kernel"))) return rc;
+  }
 
   if (!with_dw) return MVSDF_OK;
   // dW over the points
@@ -422,7 +443,7 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
                        "cudaFuncSetAttribute(mlp_bwd_dw_kernel)")))
     return rc;
   note_launch();
-  pe = prof_begin_ext(6, st);
+  void* pe = prof_begin_ext(6, st);
   mlp_bwd_dw_kernel<<<items, kDwThreads, dw_smem_bytes(), st>>>(d);
   prof_end_ext(pe, st);
   return check_cuda(cudaGetLastError(), "launch mlp_bwd_dw_kernel");

@@ -191,7 +191,7 @@ def sdf_backward(net: PackedNet, x: torch.Tensor, save: torch.Tensor, g_full, g_
     dw = torch.empty(L.mvsdf_train_dw_floats(net.handle), dtype=torch.float32, device=dev) if need_dw else None
     db = torch.empty(L.mvsdf_train_db_floats(net.handle), dtype=torch.float32, device=dev) if need_dw else None
     dx = torch.empty(n, 3, dtype=torch.float32, device=dev) if need_dx else None
-    ws_bytes = L.mvsdf_train_workspace_bytes(net.handle, n, 1) if need_dw else 256
+    ws_bytes = L.mvsdf_train_workspace_bytes(net.handle, n if need_dw else 0, 1)      # n = 0: header + sweep scratch only
     ws = _scratch("sdf_bwd", ws_bytes, dev)
     g_full = None if g_full is None else _f32(g_full)
     g_grad = None if g_grad is None else _f32(g_grad)
