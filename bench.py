@@ -171,6 +171,8 @@ def run_ours(args):
     model.skip_min_sdf = bool(args.skip_min_sdf)
     if args.prefilter_tau is not None:
         model.prefilter_tau = float(args.prefilter_tau)
+    if args.trace_screen_margin is not None:      # experiment flag (off by default): not path-identical to the reference
+        model.trace_screen_margin = float(args.trace_screen_margin)
     loss_mod = B200IDRLoss()
     L = _lib.lib()
     tp = 0.5
@@ -351,6 +353,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (>=400 MB of ray state + request lists per step)",
                        "skip_min_sdf": bool(args.skip_min_sdf),
                        "cuda_graph": bool(graphs_used),
+                       "trace_screen_margin": model.trace_screen_margin,
                        "prefilter": {"tau": model.prefilter_tau, "screened_evals_per_ray": screened / R, "refined_evals_per_ray": refined / R,
                                      "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
                                      "note": "100-sample stages: screening pass (1 fp16 product, 5 chunks of 10-30 samples, stops behind "
@@ -734,6 +737,8 @@ def main():
     ap.add_argument("--shard-tile", type=int, default=1024, help="strong scaling: rays per round-robin tile (0 = contiguous ranges)")
     ap.add_argument("--skip-min-sdf", type=int, default=0)
     ap.add_argument("--prefilter-tau", type=float, default=None, help="override B200IDRNetwork.prefilter_tau (0 = off)")
+    ap.add_argument("--trace-screen-margin", type=float, default=None,
+                    help="experiment: B200IDRNetwork.trace_screen_margin (default 0 = every sphere-tracing value exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-period", type=float, default=1.0, help="seconds between nvidia-smi clock samples on rank 0 (0 = off)")
     ap.add_argument("--no-profile", action="store_true", help="diagnostic: no per-launch CUDA events in the timed region")

@@ -114,6 +114,13 @@ typedef struct mvsdf_tracer_params {
                              are bit-identical to tau = 0 as long as the screening error stays below tau; out_counters
                              [MVSDF_CTR_VIOLATIONS] counts refined samples whose screening error exceeded tau / 2 -- a
                              caller that sees it non-zero repeats the call with tau = 0 (B200IDRNetwork does). */
+  float trace_screen_margin; /* 0 = off (default: every sphere-tracing value is exact and the march follows the reference's
+                             path step for step).  > 0: experiment of profiles/r02/exp_mixed_trace_*: a march position whose
+                             last step exceeded 2 * margin is evaluated at screening precision first and the value is used as
+                             the step when |value| > margin, otherwise the position is evaluated exactly.  Convergence,
+                             overshoot back-off, sampler and secant decisions always see exact values, but the march no
+                             longer follows the reference's path: distances agree to the convergence threshold (measured
+                             <= 5e-5 at margin 0.02), not to rounding. */
 } mvsdf_tracer_params;
 
 #define MVSDF_NUM_TRACE_COUNTERS 256

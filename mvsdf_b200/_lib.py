@@ -89,7 +89,7 @@ def _declare(lib):
         _fields_ = [("object_bounding_sphere", c_float), ("sdf_threshold", c_float), ("line_search_step", c_float),
                     ("dist_clip", c_float), ("line_step_iters", c_int), ("sphere_tracing_iters", c_int),
                     ("n_steps", c_int), ("n_secant_steps", c_int), ("skip_min_sdf", c_int),
-                    ("prefilter_tau", c_float)]
+                    ("prefilter_tau", c_float), ("trace_screen_margin", c_float)]
     lib.TracerParams = TracerParams
     lib.mvsdf_trace_workspace_bytes.restype = c_size_t
     lib.mvsdf_trace_workspace_bytes.argtypes = [c_int64, c_int]

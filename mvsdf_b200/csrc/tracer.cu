@@ -75,10 +75,12 @@ struct TraceCtx {
   int* ref_counters; // [kNumCounters]  prefilter: refined samples per 100-sample batch
   int* pf_counts;    // [kNumCounters]  prefilter: per (batch, sample chunk) active rays / points of the chunked screening pass
   int* spec_counts;  // [kNumCounters]  sphere tracing: size of the speculative back-off request list of every iteration
+  int* mix_counts;   // [kNumCounters]  mixed-precision sphere tracing: size of the screening list of every phase
   int* act_list[2];  // [batch_rays]    rays of the batch that still need their next sample chunk (ping-pong)
   int R, N;
   long long cap;
   float thr, clip, line_step;
+  float margin;      // mixed-precision sphere tracing (mvsdf_tracer_params::trace_screen_margin), 0 = off
 };
 
 __device__ __forceinline__ float3 ray_point(const float* cam, const float* dir, float t) {
@@ -97,9 +99,22 @@ __device__ __forceinline__ int push_request(const TraceCtx& c, int counter, floa
 
 __device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf(v, -lim), lim); }
 
+// Mixed-precision sphere tracing (trace_screen_margin > 0, off by default): a march position whose last step was long is
+// first evaluated at screening precision (list ref_pts, owner (2 ray + end) in ref_src); trace_triage_kernel accepts the
+// value when it is clearly outside the margin and queues the position for the exact evaluation otherwise.
+__device__ __forceinline__ int push_march(const TraceCtx& c, int counter, int mix_ctr, bool far, int owner, float3 p) {
+  if (!far) return push_request(c, counter, p);
+  const int i = atomicAdd(c.mix_counts + mix_ctr, 1);
+  c.ref_pts[3 * (size_t)i + 0] = p.x;
+  c.ref_pts[3 * (size_t)i + 1] = p.y;
+  c.ref_pts[3 * (size_t)i + 2] = p.z;
+  c.ref_src[i] = owner;
+  return -1;
+}
+
 // ---- a1 + a2 + tracer initialisation (rend_util.py:48-100, :141-162; ray_tracing.py:104-137)
 __global__ void ray_setup_kernel(TraceCtx c, const float* __restrict__ uv, const float* __restrict__ pose,
-                                 const float* __restrict__ intr, float* __restrict__ cam_out, float radius, int counter) {
+                                 const float* __restrict__ intr, float* __restrict__ cam_out, float radius, int counter, int mix_ctr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= c.R) return;
   const int b = r / c.N;
@@ -151,8 +166,8 @@ __global__ void ray_setup_kernel(TraceCtx c, const float* __restrict__ uv, const
   c.s.cur_e[r] = 0.f;
   int ss = -1, se = -1;
   if (fl) {
-    ss = push_request(c, counter, ray_point(cam, d, t0));
-    se = push_request(c, counter, ray_point(cam, d, t1));
+    ss = push_march(c, counter, mix_ctr, c.margin > 0.f, 2 * r, ray_point(cam, d, t0));
+    se = push_march(c, counter, mix_ctr, c.margin > 0.f, 2 * r + 1, ray_point(cam, d, t1));
   }
   c.s.slot_s[r] = ss;
   c.s.slot_e[r] = se;
@@ -209,7 +224,7 @@ __device__ __forceinline__ void resolve_backoff(const TraceCtx& c, int r, uint32
 }
 
 // top of the while-loop body (ray_tracing.py:139-171); `first`: no end-of-body update yet; `last`: iters == max
-__global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter, int n_k, int backoff_ctr) {
+__global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter, int n_k, int backoff_ctr, int mix_ctr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= c.R) return;
   uint32_t fl = c.s.flags[r];
@@ -238,10 +253,45 @@ __global__ void trace_top_kernel(TraceCtx c, int first, int last, int counter, i
     const float* d = c.s.dir + 3 * (size_t)r;
     c.s.next_s[r] = 0.f;
     c.s.next_e[r] = 0.f;
-    if (fl & F_LIVE_S) c.s.slot_s[r] = push_request(c, counter, ray_point(cam, d, acc_s));
-    if (fl & F_LIVE_E) c.s.slot_e[r] = push_request(c, counter, ray_point(cam, d, acc_e));
+    // mixed precision: the step just taken predicts the next value (it shrinks geometrically towards the surface)
+    const float far_step = 2.0f * c.margin;
+    if (fl & F_LIVE_S) c.s.slot_s[r] = push_march(c, counter, mix_ctr, c.margin > 0.f && cur_s > far_step, 2 * r, ray_point(cam, d, acc_s));
+    if (fl & F_LIVE_E) c.s.slot_e[r] = push_march(c, counter, mix_ctr, c.margin > 0.f && cur_e > far_step, 2 * r + 1, ray_point(cam, d, acc_e));
   }
   c.s.flags[r] = fl;
+}
+
+// mixed-precision sphere tracing: screening values clearly outside the margin become the march's next SDF value, the rest
+// join the exact request list of the same phase.  `accepted_ctr` is the E_trace slot of the accepted evaluations (the
+// reference requests them too; the exact list only counts the others).
+__global__ void trace_triage_kernel(TraceCtx c, int mix_ctr, int counter, int accepted_ctr) {
+  const int n = c.mix_counts[mix_ctr];
+  int accepted = 0, refined = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int owner = c.ref_src[i];
+    const int r = owner >> 1;
+    const float fs = clampf(c.ref_val[i], c.clip);
+    if (fabsf(fs) > c.margin) {
+      if (owner & 1) c.s.next_e[r] = fs;
+      else c.s.next_s[r] = fs;
+      ++accepted;
+    } else {
+      const int slot = push_request(c, counter, make_float3(c.ref_pts[3 * (size_t)i], c.ref_pts[3 * (size_t)i + 1], c.ref_pts[3 * (size_t)i + 2]));
+      if (owner & 1) c.s.slot_e[r] = slot;
+      else c.s.slot_s[r] = slot;
+      ++refined;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    accepted += __shfl_xor_sync(0xffffffffu, accepted, o);
+    refined += __shfl_xor_sync(0xffffffffu, refined, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (accepted) atomicAdd(c.counters + accepted_ctr, accepted);
+    if (accepted + refined) atomicAdd(c.counters + kCtrScreened, accepted + refined);
+    if (refined) atomicAdd(c.counters + kCtrRefined, refined);
+  }
 }
 
 // one pass of the overshoot back-off loop (ray_tracing.py:173-191), sequential form: used when the request list cannot hold
@@ -673,7 +723,7 @@ static WorkspaceLayout layout_for(int64_t R, int B, int batch_rays) {
     off += (bytes + 255) / 256 * 256;
     return o;
   };
-  w.off_counters = take(4 * kNumCounters * 4);
+  w.off_counters = take(5 * kNumCounters * 4);
   w.off_cam = take((size_t)B * 3 * 4);
   for (int i = 0; i < 9; ++i) w.off_f[i] = take((size_t)R * 4);       // acc_s acc_e min max next_s next_e cur_s cur_e z
   for (int i = 0; i < 4; ++i) w.off_i[i] = take((size_t)R * 4);       // slot_s slot_e list list_pos
@@ -722,7 +772,8 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     // fixed slots (and from there into the prefilter's counters) BEFORE anything is launched
     const int64_t batches = (R + (1 << 18) - 1) / (1 << 18);
     const int64_t need = 1 + (int64_t)prm->sphere_tracing_iters * (1 + prm->line_step_iters) + batches + prm->n_secant_steps +
-                         ((training && !prm->skip_min_sdf) ? batches : 0);
+                         ((training && !prm->skip_min_sdf) ? batches : 0) +
+                         (prm->trace_screen_margin > 0.f ? 1 + prm->sphere_tracing_iters : 0);
     if (need >= kCtrScreened)
       return fail(MVSDF_ERR_INVALID,
                   "mvsdf_trace: %lld request phases (1 + sphere_tracing_iters*(1+line_step_iters) + sampler/min-sdf batches + "
@@ -760,6 +811,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.ref_counters = c.counters + kNumCounters;
   c.pf_counts = c.counters + 2 * kNumCounters;
   c.spec_counts = c.counters + 3 * kNumCounters;
+  c.mix_counts = c.counters + 4 * kNumCounters;
   for (int i = 0; i < 2; ++i) c.act_list[i] = reinterpret_cast<int*>(ws + w.off_act[i]);
   c.R = (int)R;
   c.N = n_pixels;
@@ -767,8 +819,9 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   c.thr = prm->sdf_threshold;
   c.clip = prm->dist_clip;
   c.line_step = prm->line_search_step;
+  c.margin = prm->trace_screen_margin > 0.f ? prm->trace_screen_margin : 0.f;
 
-  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 4 * kNumCounters * 4, st), "memset counters");
+  int rc = check_cuda(cudaMemsetAsync(c.counters, 0, 5 * kNumCounters * 4, st), "memset counters");
   if (rc) return rc;
   const int grid_r = (int)((R + kBlock - 1) / kBlock);
   int ctr = 0;   // every request phase uses its own counter: no resets, no host round trips
@@ -794,8 +847,19 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
     ++ref_ctr;
     return (int)MVSDF_OK;
   };
-  note_launch(); ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr);
-  if ((rc = eval(ctr++))) return rc;
+  // sphere-tracing phase: (mixed precision only: screening pass over the far positions + triage, then) the exact pass
+  int mix_ctr = 0;
+  auto eval_march = [&](int counter) {
+    if (c.margin > 0.f) {
+      int e = mlp_sdf(net, packed, c.ref_pts, 0, c.mix_counts + mix_ctr, MVSDF_HEAD_SDF_ONLY, c.ref_val, nullptr, nullptr, false, st, true);
+      if (e) return e;
+      note_launch(); trace_triage_kernel<<<sm_count() * 4, kBlock, 0, st>>>(c, mix_ctr, counter, ctr++);
+      ++mix_ctr;
+    }
+    return eval(counter);
+  };
+  note_launch(); ray_setup_kernel<<<grid_r, kBlock, 0, st>>>(c, uv, pose, intrinsics, cam, prm->object_bounding_sphere, ctr, mix_ctr);
+  if ((rc = eval_march(ctr++))) return rc;
   const int n_k = prm->line_step_iters;
   // worst case every ray overshoots at both ends: 2 R n_k candidates must fit the request list; MVSDF_SPEC_BACKOFF=0 forces
   // the sequential form (A/B)
@@ -803,8 +867,8 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   const bool speculative = spec_env && 2ll * R * n_k <= c.cap;
   int backoff_ctr = 0;      // E_trace slot of the previous iteration's back-off evaluations (filled by the next trace_top_kernel)
   for (int it = 0; it < prm->sphere_tracing_iters; ++it) {
-    note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr, n_k, backoff_ctr);
-    if ((rc = eval(ctr++))) return rc;
+    note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr, n_k, backoff_ctr, mix_ctr);
+    if ((rc = eval_march(ctr++))) return rc;
     if (n_k > 0 && speculative) {
       // the whole back-off loop of this iteration in one launch (resolve_backoff)
       note_launch(); trace_backoff_spec_kernel<<<grid_r, kBlock, 0, st>>>(c, n_k, c.spec_counts + it);
@@ -818,7 +882,7 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
       }
     }
   }
-  note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr, n_k, backoff_ctr);
+  note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, prm->sphere_tracing_iters == 0, 1, ctr, n_k, backoff_ctr, mix_ctr);
   const int list_ctr = kCtrSamplerRays;
   note_launch(); trace_finish_kernel<<<grid_r, kBlock, 0, st>>>(c, list_ctr);
   // sampler in batches of batch_rays rays (worst case: every ray unconverged)

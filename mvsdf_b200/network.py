@@ -306,6 +306,9 @@ class B200IDRNetwork(nn.Module):
         # un-refined ones (re-evaluated exactly for this purpose only) -- a statistical monitor, not a proof
         self.prefilter_tau = float(os.environ.get("MVSDF_PREFILTER_TAU", DEFAULT_PREFILTER_TAU))
         self.prefilter_fallbacks = 0       # forwards repeated exactly because the screening guard tripped
+        # experiment, off by default (include/mvsdf_b200.h, trace_screen_margin; profiles/r02/exp_mixed_trace_*): long
+        # sphere-tracing steps at screening precision.  Not path-identical to the reference any more.
+        self.trace_screen_margin = float(os.environ.get("MVSDF_TRACE_SCREEN_MARGIN", 0.0))
         self._ws: Dict[str, torch.Tensor] = {}
         self.last_trace_counters: Optional[torch.Tensor] = None
         # CUDA graphs: the launch sequence of a forward is static and sync-free (device-side counts everywhere), so for
@@ -347,6 +350,7 @@ class B200IDRNetwork(nn.Module):
         p.n_secant_steps = c["n_secant_steps"]
         p.skip_min_sdf = 1 if self.skip_min_sdf else 0
         p.prefilter_tau = self.prefilter_tau
+        p.trace_screen_margin = self.trace_screen_margin
         return p
 
     def trace(self, sdf_net, uv, pose, intrinsics, object_mask_u8, training: bool, steps01=None):
@@ -719,7 +723,7 @@ class B200IDRNetwork(nn.Module):
         dev = live[0].device
         pkey = tuple(p.data_ptr() for p in self.parameters())
         tkey = tuple(sorted(self.tracer_conf.items())) + (os.environ.get("IDR_USE_ENV", "0"), os.environ.get("IDR_RENDER", "0"))
-        key = (tag, training, bool(self.skip_min_sdf), float(self.prefilter_tau), str(dev), pkey, tkey,
+        key = (tag, training, bool(self.skip_min_sdf), float(self.prefilter_tau), float(self.trace_screen_margin), str(dev), pkey, tkey,
                tuple(None if t is None else (tuple(t.shape), t.dtype) for t in live))
         g = self._graphs.get(key)
         if g is None:
