@@ -409,11 +409,21 @@ def run_train(args):
     from mvsdf_b200.network import B200IDRNetwork, default_conf
     from mvsdf_b200.optim import B200Adam
 
-    assert args.gpus == 1, "the training-step bench is a single-GPU line"
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    import torch.distributed as dist
+    from mvsdf_b200 import parallel
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        # data-parallel training ("for end-to-end DP training add a gradient all-reduce"): every rank steps
+        # on its OWN 8 images x 4096 rays, the gradients are averaged with one NCCL all-reduce of a flat fp32 bucket, every rank
+        # applies the same Adam update.  Weak scaling: the global batch grows with N.
+        dist.init_process_group("nccl", device_id=dev)
     cfg = WORKLOADS[args.workload]
-    scene, sd = make_inputs(cfg, 0, 1, shard=False)
+    scene, sd = make_inputs(cfg, rank, world, shard=False)
     B, N = scene["uv"].shape[:2]
     R = B * N
     tp = 0.5
@@ -422,9 +432,10 @@ def run_train(args):
     model.train()
     model.skip_min_sdf = bool(args.skip_min_sdf)
     loss_mod = B200IDRLoss()
-    opt = B200Adam(model.parameters(), lr=2.0e-4 * B)            # idr_train.py:110-113: lr scaled by the batch size
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = B200Adam(params, lr=2.0e-4 * B * world)                # idr_train.py:110-113: lr scaled by the (global) batch size
     L = _lib.lib()
-    g = torch.Generator().manual_seed(1234)
+    g = torch.Generator().manual_seed(1234 + rank)
     steps01 = torch.rand(100, generator=g)
     eik = torch.rand(R // 2, 3, generator=g) * 2 - 1
     host = pin({k: scene[k] for k in IN_KEYS + TRAIN_GT_KEYS})
@@ -435,15 +446,30 @@ def run_train(args):
         out = model({k: inputs[k] for k in IN_KEYS + ["depths", "depth_cams", "size", "center"]}, tp, steps01=steps01, eik_points=eik)
         ls = loss_mod(out, {k: inputs[k] for k in TRAIN_GT_KEYS}, tp, B)
         opt.zero_grad(set_to_none=True)
-        ls["loss"].sum().backward()
+        (ls["loss"].sum() / world).backward()
+        if world > 1:
+            parallel.allreduce_gradients(params)       # SUM of the 1/world-scaled gradients = their mean
         opt.step(max_grad_norm=cap)
         return out, ls
 
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     for _ in range(args.warmup):
         step(resident)
-    torch.cuda.synchronize(dev)
-    clocks = ClockSampler(0)
-    clocks.start()
+    barrier()
+    clocks = ClockSampler(local, args.clock_period) if (rank == 0 and args.clock_period > 0) else None
+    if clocks:
+        clocks.start()
     launches0 = L.mvsdf_launch_count()
     L.mvsdf_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -451,9 +477,9 @@ def run_train(args):
     for _ in range(args.steps):
         out, ls = step(resident)
     e1.record()
-    torch.cuda.synchronize(dev)
-    ms_per_step = e0.elapsed_time(e1) / args.steps
-    clk = clocks.stop()
+    barrier()
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clk = clocks.stop() if clocks else None
     launches = L.mvsdf_launch_count() - launches0
     ms_kind = (ctypes.c_float * 8)()
     n_kind = (ctypes.c_int * 8)()
@@ -475,13 +501,17 @@ def run_train(args):
 
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in step_keys)
     h2d_step()
-    torch.cuda.synchronize(dev)
+    barrier()
     e0.record()
     for _ in range(args.steps):
         lv = h2d_step()
     e1.record()
-    torch.cuda.synchronize(dev)
-    ms_e2e = e0.elapsed_time(e1) / args.steps
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
 
     width = cfg["width"]
     fl = FLOP[width]
@@ -493,23 +523,26 @@ def run_train(args):
     peaks = load_peaks()
     achieved = bwd_flops / (ms_bwd * 1e-3) / 1e12 if ms_bwd > 0 else None
     base = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             base = torch_cuda_port_train_sample(cfg, scene, sd, dev, tp, steps01, eik)
         except Exception as e:
             base = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     line = {
         "metric": "rays/sec (training step: forward + 5 losses + backward + Adam) at 8 x 4096 rays, DTU-shaped",
-        "value": R / (ms_per_step * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "value": world * R / (ms_per_step * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32-equivalent (fp16 hi/lo split operands, fp32 tensor-core accumulate), fp32 Adam", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {B} images x {N} rays, {cfg['n_src']} src views, 8x{width} SDF MLP + 4x{width} render "
                                f"MLP, train_progress {tp}: IDRNetwork.forward(train) + IDRLoss.forward (rgb, eikonal, surf, feat, depth) "
                                f"+ backward + Adam(lr 2e-4 x {B}, grad cap {cap})",
-                   "rays": R, "hit_fraction": n_hit / R, "tracer_evals_per_ray": evals / R, "skip_min_sdf": bool(args.skip_min_sdf),
+                   "rays": R * world, "rays_per_gpu": R,
+                   "parallelism": (f"dp{world}: every rank steps on its own {B} images, gradients averaged with one NCCL all-reduce of a flat "
+                                   f"fp32 bucket, identical Adam update on every rank") if world > 1 else "single GPU",
+                   "hit_fraction": n_hit / R, "tracer_evals_per_ray": evals / R, "skip_min_sdf": bool(args.skip_min_sdf),
                    "swept_points": swept, "l2_policy": "inputs + saved activations (>= 2 GB per step) larger than L2"},
         "clocks": clk,
-        "e2e": {"value": R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
+        "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 + 4 * 7},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "mlp_bwd_sweep_pair_kernel + mlp_bwd_dw_kernel (reverse sweep and dW GEMM of both MLPs)",

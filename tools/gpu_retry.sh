@@ -1,8 +1,8 @@
 #!/bin/bash
-# usage: tools/gpu_retry.sh <timeout_s> '<command>'  -- retries gpurun while the pod answers "busy" (nothing is charged)
+# usage: [GPUS=2|4|8] tools/gpu_retry.sh <timeout_s> '<command>'  -- retries gpurun while the pod answers "busy" (nothing is charged)
 T=$1; shift
 for i in $(seq 1 12); do
-  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@" > /tmp/gpu_retry_last.log 2>&1
+  /usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$T" -- "$@" > /tmp/gpu_retry_last.log 2>&1
   rc=$?
   if grep -q "status=transient" /tmp/gpu_retry_last.log; then sleep 120; continue; fi
   cat /tmp/gpu_retry_last.log; exit $rc
