@@ -387,7 +387,8 @@ static int run_backward(const mvsdf_net* net, const void* packed_t, const float*
 
   const size_t smem = mlp_smem_bytes(t.k_cores_max);
   // batches that fill every SM twice run the CTA-pair sweep (half the weight stream per SM); MVSDF_PAIR_SWEEP=0 keeps the single-CTA one
-  static const bool pair_env = [] { const char* e = getenv("MVSDF_PAIR_SWEEP"); return !(e && e[0] == '0'); }();
+  const char* pair_e = getenv("MVSDF_PAIR_SWEEP");       // read per call: the A/B test toggles it
+  const bool pair_env = !(pair_e && pair_e[0] == '0');
   const int max_pairs = std::min(sms / 2, 128);
   if (pair_env && n_tiles >= 2LL * sms) {
     auto kern = mlp_bwd_sweep_pair_kernel<KIND, MODE>;
