@@ -269,7 +269,8 @@ int mvsdf_pack_weights_t(const mvsdf_net* net, const float* const* weight_v_host
 int mvsdf_sdf_forward_train(const mvsdf_net* net, const void* packed, const float* x, int64_t n, size_t save_bytes, void* save,
                             float* out_full, float* out_grad, void* stream);
 /* g_full [n, 2+F] = dL/d full, g_grad [n,3] = dL/d grad (either may be NULL = zero); out_dx [n,3] optional = dL/dx.
- * out_dw = out_db = NULL: dx-only sweep (no gradient dumps, no dW GEMM; the workspace needs 256 bytes) -- the first of the two
+ * out_dw = out_db = NULL: dx-only sweep (no gradient dumps, no dW GEMM; the workspace needs mvsdf_train_workspace_bytes(net, 0, with_grad)
+ *      bytes: the scale header + the CTA-pair sweep's scratch) -- the first of the two
  * sweeps over the surface points, whose only purpose is dL/d x_diff for the implicit-differentiation term. */
 int mvsdf_sdf_backward(const mvsdf_net* net, const void* packed_t, const float* x, int64_t n, const void* save, const float* g_full,
                        const float* g_grad, size_t workspace_bytes, void* workspace, float* out_dx, float* out_dw, float* out_db,
