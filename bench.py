@@ -121,8 +121,8 @@ def make_inputs(cfg, rank, world=1, shard=None, tile=1024):
     Strong scaling (shard): all ranks hold the SAME image and rank r takes its share of the rays -- round-robin tiles of
     `tile` consecutive rays (tile 0: one contiguous range) -- with the feature maps replicated."""
     shard = bool(cfg.get("shard_rays")) if shard is None else shard
-    scene = synth.make_scene(cfg["H"], cfg["W"], n_images=cfg["n_images"], n_src=cfg["n_src"], n_rays=cfg["n_rays"],
-                             seed=0 if shard else rank)
+    seed = int(os.environ.get("MVSDF_BENCH_SEED", 0 if shard else rank))       # env: diagnostic (replay another rank's scene)
+    scene = synth.make_scene(cfg["H"], cfg["W"], n_images=cfg["n_images"], n_src=cfg["n_src"], n_rays=cfg["n_rays"], seed=seed)
     if shard and world > 1:
         from mvsdf_b200 import parallel
         scene = parallel.shard_rays(scene, rank, world, tile=tile)
@@ -540,6 +540,9 @@ def run_train(args):
                    "parallelism": (f"dp{world}: every rank steps on its own {B} images, gradients averaged with one NCCL all-reduce of a flat "
                                    f"fp32 bucket, identical Adam update on every rank") if world > 1 else "single GPU",
                    "hit_fraction": n_hit / R, "tracer_evals_per_ray": evals / R, "skip_min_sdf": bool(args.skip_min_sdf),
+                   "prefilter": {"tau": model.prefilter_tau, "exact_fallbacks": model.prefilter_fallbacks,
+                                 "note": "a step whose screening guard trips is repeated without the prefilter and tau is doubled "
+                                         "(B200IDRNetwork._redo_exact); such steps are inside the timed region"},
                    "swept_points": swept, "l2_policy": "inputs + saved activations (>= 2 GB per step) larger than L2"},
         "clocks": clk,
         "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,

@@ -56,6 +56,10 @@ void* prof_begin_ext(int kind, cudaStream_t st);
 void prof_end_ext(void* p, cudaStream_t st);
 static ProfEvent* prof_begin(int kind, cudaStream_t st) {
   if (!g_prof_on) return nullptr;
+  // a launch that is being captured into a CUDA graph is not timed: an event recorded during capture becomes a graph node
+  // and can never be synchronised on (a forward repeated without the prefilter captures a new graph mid-measurement)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
   if (g_prof_used == g_prof_pool.size()) {
     ProfEvent p{};
     if (cudaEventCreate(&p.e0) != cudaSuccess || cudaEventCreate(&p.e1) != cudaSuccess) return nullptr;
