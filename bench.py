@@ -355,6 +355,8 @@ def run_ours(args):
                        "cuda_graph": bool(graphs_used),
                        "trace_screen_margin": model.trace_screen_margin,
                        "prefilter": {"tau": model.prefilter_tau, "screened_evals_per_ray": screened / R, "refined_evals_per_ray": refined / R,
+                                     "sampler_rays_fraction": int(cnt[_lib.CTR_SAMPLER_RAYS]) / R,
+                                     "minsdf_rays_fraction": int(cnt[_lib.CTR_MINSDF_RAYS]) / R,
                                      "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
                                      "note": "100-sample stages: screening pass (1 fp16 product, 5 chunks of 10-30 samples, stops behind "
                                              "the first certainly negative sample) + exact pass (3 products) over the undecidable "
