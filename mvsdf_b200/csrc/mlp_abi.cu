@@ -240,6 +240,13 @@ static int launch_mlp_pair(const NetPlan& p, MlpArgs& a, long long pair_tiles, b
   constexpr bool kCanLp = KIND == NET_SDF && MODE == 0 && VER == 2;
   // the saving instantiation exists for the two training forwards: SDF value+gradient and the rendering net
   constexpr bool kCanSave = (KIND == NET_SDF && MODE == 1) || (KIND == NET_RENDER && MODE == 0);
+  // exact SDF-only evaluations: the one-row head runs as a dot product in the last hidden layer's epilogue (MVSDF_FUSE_HEAD=0:
+  // as an UMMA layer like every other head; read per call, the A/B test toggles it)
+  const char* fuse_e = getenv("MVSDF_FUSE_HEAD");
+  a.fuse_head = (VER == 2 && KIND == NET_SDF && MODE == 0 && !a.lp && !a.save && a.head == HEAD_SDF_ONLY && a.n_run >= 2 &&
+                 !(fuse_e && fuse_e[0] == '0'))
+                    ? 1
+                    : 0;
   auto kern = (kCanLp && a.lp) ? mlp_pair2_kernel<KIND, MODE, kCanLp ? 1 : 0>
                                : ((kCanSave && a.save) ? mlp_pair2_kernel<KIND, MODE, 0, kCanSave ? 1 : 0> : mlp_pair2_kernel<KIND, MODE, 0>);
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

@@ -52,6 +52,7 @@ struct MlpArgs {
   int debug;                 // bit0 skip weight copies, bit1 skip UMMAs, bit2 skip epilogue math (bottleneck isolation only)
   int feat_stride;           // row stride (floats) of `feats`; lets the render pass read full[:, 2:] in place
   int lp;                    // screening precision (pair2 kernel only): W_hi X_hi^T, see mlp_pair2_kernel.cuh
+  int fuse_head;             // pair2 kernel, exact SDF-only head: the 1-row head is a dot product in the last hidden layer's epilogue
   long long n;               // number of points (ignored when n_ptr != nullptr)
   const int* n_ptr;          // optional device-side count
   const float* x;            // [n,3]
@@ -72,8 +73,9 @@ struct MlpArgs {
   LayerPlan L[10];
 };
 
+constexpr int kHeadPartBytes = 8 * kTileN * 4;     // fused SDF head (pair2 kernel): partial sums [rows' CTA][lane quarter][my 64 columns]
 __host__ __device__ inline size_t mlp_smem_bytes(int k_cores_max) {
-  return (size_t)kStages * kStageBytes + (size_t)k_cores_max * kBCoreStride + kPeTileBytes + 256;
+  return (size_t)kStages * kStageBytes + (size_t)k_cores_max * kBCoreStride + kPeTileBytes + 256 + kHeadPartBytes;
 }
 
 // Range monitor: activations are stored as fp16 hi/lo of kActScale * x, so |x| >= 1023 overflows to inf; the split then

@@ -86,6 +86,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
   const uint32_t bar_px = bar_lx + 16;                    // 2 (leader only): the peer's bar_lx[h] completed
   const uint32_t bar_d1 = bar_px + 16;                    // (leader only) accumulator 1 drained to registers in BOTH CTAs
   const uint32_t s_tmem = bar_d1 + 8;
+  const uint32_t bar_head = s_tmem + 8;                   // fused head: 16 local warps + the peer's partial sums (st.async bytes)
+  const uint32_t s_part = s_bar + 256;                    // fused head: float [8 = rows' CTA * 4 + lane quarter][64 columns of mine]
+  // Fused head (exact SDF-only evaluations): the head layer has ONE output row, but as an UMMA it costs two full parts
+  // (M = 256 rows, K = 512: 6.6 % of a tile's tensor time).  Instead the epilogue of the last hidden layer multiplies its
+  // fp32 softplus outputs with the head weight of its feature, reduces over the 32 features of the warp with a shuffle
+  // butterfly (the same tree for every column, so a point's value does not depend on where it sits), adds the two 256-row
+  // stages, and leaves one partial sum per (rows' CTA, lane quarter, column); thread c of the column's own CTA adds the
+  // eight partials in a fixed order.  The activations never pass through the fp16 split on this path.
+  constexpr bool kCanFuse = KIND == NET_SDF && MODE == 0 && LP == 0 && SAVE == 0;
+  const bool fuse = kCanFuse && a.fuse_head != 0;
+  const int n_mma = fuse ? a.n_run - 1 : a.n_run;         // layers that run on the tensor cores
   uint8_t* const g_scratch = (KIND == NET_SDF) ? (smem + kStages * kStageBytes) : (smem + kStages * kStageBytes + xbytes);
   float* const scratch = reinterpret_cast<float*>(g_scratch);
 
@@ -110,6 +121,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     ptx::mbar_init(bar_px, 1);
     ptx::mbar_init(bar_px + 8, 1);
     ptx::mbar_init(bar_d1, 2 * kEpiWarps);
+    ptx::mbar_init(bar_head, kEpiWarps);
     ptx::fence_mbar_init();
   }
   if (warp == kEpiWarps + 1) {
@@ -126,7 +138,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     // ------------------------------------------------------------------ weight producer: my 128-row half, in UMMA order
     uint32_t it = 0;
     for (long long g = pair0; g < n_tiles; g += pair_stride) {
-      for (int l = 0; l < a.n_run; ++l) {
+      for (int l = 0; l < n_mma; ++l) {
         const LayerPlan& lp = a.L[l];
         for (int part = 0; part < 4; ++part) {
           int mp, k0, k1;
@@ -181,7 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     constexpr uint32_t dhi_b = (128u >> 4) | (1u << 14);
     int tr = 0;
     for (long long g = pair0; g < n_tiles; g += pair_stride) {
-      for (int l = 0; l < a.n_run; ++l, tr += 8) {
+      for (int l = 0; l < n_mma; ++l, tr += 8) {
         const LayerPlan& lp = a.L[l];
         if (lane == 0) P2_TRACE(0, tr);
         for (int part = 0; part < 4; ++part) {
@@ -269,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     const uint32_t remote_full = ptx::mapa(bar_full, 0);
     uint32_t it = 0;
     for (long long g = pair0; g < n_tiles; g += pair_stride) {
-      for (int l = 0; l < a.n_run; ++l) {
+      for (int l = 0; l < n_mma; ++l) {
         const LayerPlan& lp = a.L[l];
         int n_stage = 0;
         for (int part = 0; part < 4; ++part) {
@@ -291,7 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     const uint32_t remote_px = ptx::mapa(bar_px, 0);
     uint32_t x_ctr = 0;
     for (long long g = pair0; g < n_tiles; g += pair_stride) {
-      for (int l = 0; l < a.n_run; ++l) {
+      for (int l = 0; l < n_mma; ++l) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           ptx::mbar_wait(bar_lx + 8 * h, x_ctr & 1);
@@ -317,6 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
     const uint32_t remote_d1 = ptx::mapa(bar_d1, 0);
     constexpr float kInvScale = 1.0f / (kWeightScale * kActScale);
     uint32_t acc_ctr[kP2Tiles] = {0, 0};
+    uint32_t head_ctr = 0;
     int tr = 0;
     const bool tracer = threadIdx.x == 0;
 
@@ -431,12 +444,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
 
       if (tracer) P2_TRACE(1 + crank, tr - 7);        // prologue done
       // ---------------- layers
-      for (int l = 0; l < a.n_run; ++l, tr += 8) {
+      for (int l = 0; l < n_mma; ++l, tr += 8) {
         const LayerPlan& lp = a.L[l];
-        const bool last = (l == a.n_run - 1);
+        const bool last = (l == n_mma - 1);
         const int n_pair_tiles = (lp.m_tiles + 1) >> 1;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool skip_src = KIND == NET_SDF && l == a.skip_layer - 1;
+        float head_acc = 0.0f;            // fused head: lane L = partial sum of column (L & 15) of the peer (L < 16) / my half
         float bias_r[kP2Tiles];
 #pragma unroll
         for (int mp = 0; mp < kP2Tiles; ++mp) {
@@ -479,9 +493,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
             }
             const bool write = have && !(skip_src && f >= a.skip_rows_begin);
             const uint32_t o0 = xoff(lcol0, f);
+            float head_w = 0.0f;
+            if (kCanFuse && fuse && last && have) {
+              // row 0 of the head layer's packed tile (hi + lo = kWeightScale * w_head[f]): K chunk f / 32, core f % 32 / 8
+              const LayerPlan& hl = a.L[a.n_run - 1];
+              const uint8_t* wt = a.packed + hl.w_off + (size_t)(f >> 5) * kStageBytes + ((f & 31) >> 3) * 128 + (f & 7) * 2;
+              head_w = __half2float(*reinterpret_cast<const __half*>(wt)) + __half2float(*reinterpret_cast<const __half*>(wt + kTileBytes));
+            }
 #pragma unroll
             for (int hcol = 0; hcol < 2; ++hcol) {
               const uint32_t dest_h = hcol == 0 ? (crank ^ 1u) : crank;     // peer columns first: their st.async overlaps my own half
+              if (kCanFuse && fuse && last) {
+                // this thread's 16 products  w_head[f] * softplus(z[f, column])  (scaled by kWeightScale * kActScale) ...
+                constexpr float kK = kInvScale * kSpT;
+                const float bias_k = bias * kSpT;
+                float hprod[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float t0 = fmaf(__uint_as_float(va[hcol][j]), kK, fmaf(__uint_as_float(vb[hcol][j]), kK, bias_k));
+                  hprod[j] = have ? head_w * softplus_t_scaled(t0) : 0.0f;
+                }
+                // ... summed over the warp's 32 features: lanes L and L ^ 16 first add their 16 values, then every step halves
+                // the values a lane keeps (those whose index has the lane's bit), so lane L ends with the total of column L & 15
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hprod[j] += __shfl_xor_sync(0xffffffffu, hprod[j], 16);
+#pragma unroll
+                for (int sft = 8, nv = 16; sft >= 1; sft >>= 1, nv >>= 1) {
+                  const bool upper = (lane & sft) != 0;
+#pragma unroll
+                  for (int i = 0; i < nv / 2; ++i) {
+                    const float send = upper ? hprod[i] : hprod[i + nv / 2];
+                    const float keep = upper ? hprod[i + nv / 2] : hprod[i];
+                    hprod[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                  }
+                }
+                if ((lane >= 16) == (hcol == 1)) head_acc += hprod[0];     // lanes 0-15 carry the peer's columns, 16-31 mine
+                continue;
+              }
               if (!last) {
                 uint32_t phi[8], plo[8];
                 if (MODE == 0) {
@@ -639,6 +687,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1) mlp_p
               if (tracer) P2_TRACE(1 + crank, tr + 4 * mp + 3);    // E_mp done (arrived)
             }
           }
+        }
+        if (kCanFuse && fuse && last) {
+          // partial sums of this warp's 32 rows (both 256-row stages): my half's columns stay here, the peer's travel;
+          // slot = CTA that owns the ROWS (not local / remote), so both CTAs add the eight partials in the same order
+          const uint32_t slot = (crank * 4u + (uint32_t)q) * (kTileN * 4) + (uint32_t)(lcol0 + (lane & 15)) * 4;
+          if (lane >= 16) ptx::st_shared_f32(s_part + slot, head_acc);
+          else ptx::st_async_b32(ptx::mapa(s_part, crank ^ 1u) + slot, __float_as_uint(head_acc), ptx::mapa(bar_head, crank ^ 1u));
+          __syncwarp();
+          if (lane == 0) {
+            if (warp == 0) ptx::mbar_arrive_expect_tx(bar_head, kEpiWarps * 16 * 4);     // the peer's 16 warps x 16 columns x 4 B
+            else ptx::mbar_arrive(bar_head);
+          }
+          if (t < kTileN) {
+            ptx::mbar_wait(bar_head, head_ctr & 1);
+            float sdf = __ldg(a.bias + a.L[a.n_run - 1].bias_off);
+            float acc = 0.0f;
+#pragma unroll
+            for (int sidx = 0; sidx < 8; ++sidx) acc += ptx::ld_shared_f32(s_part + (uint32_t)(sidx * kTileN + t) * 4);
+            sdf = fmaf(acc, kInvScale, sdf);
+            const long long gp = p0 + t;
+            if (gp < n_pts) a.out_sdf[gp] = checked(sdf, a.status);
+          }
+          ++head_ctr;
         }
       }
     }

@@ -140,9 +140,10 @@ def _subsample_parity(model, scene, dev, n_sub, seed, full_out=None):
             want = full_out[k][idx.to(dev)] if k != "diff_surf_pts" else full_out["points"][idx.to(dev)][out["network_object_mask"]]
             assert _same(want, out[k]), f"{k}: sub-sample run differs from the full-image run"
         # sdf_output is the one launch with a host-known count: 4 096 points take the single-CTA scheduling of the tile
-        # core (mlp_kernel.cuh), 1.92 M the CTA-pair kernel, whose softplus is formulated differently -- same value to fp32
-        # rounding, not the same bits
-        gate("sdf_output_small_vs_pair_kernel", (full_out["sdf_output"][idx.to(dev)] - out["sdf_output"]).abs().max().item(), 2e-6)
+        # core (mlp_kernel.cuh), 1.92 M the CTA-pair kernel, whose softplus is formulated differently and whose one-row head
+        # is an fp32 dot product in the last hidden layer's epilogue instead of an UMMA over fp16 hi/lo activations -- same
+        # value to fp32 rounding of a 512-term sum (measured 4.5e-6; both are within 2e-5 of the fp64 oracle), not the same bits
+        gate("sdf_output_small_vs_pair_kernel", (full_out["sdf_output"][idx.to(dev)] - out["sdf_output"]).abs().max().item(), 1.5e-5)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     with torch.no_grad():
         ref = O.idr_forward(O.sdf_weights(sd), O.render_weights(sd), sub, None, False)

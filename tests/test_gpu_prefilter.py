@@ -88,7 +88,9 @@ def test_forward_guard_falls_back_to_exact():
     # the widening converges: after a few steps the guard is quiet and the outputs are still the exact ones
     for _ in range(12):
         out = model(inp)
-    assert 1e-3 <= model.prefilter_tau <= 2.5e-2 and int(model.last_trace_counters[255]) == 0
+    # (where the doubling stops depends on whether the scene's largest |screening - exact| sits just below or just above a
+    #  power-of-two multiple of the threshold: 6.4e-4 or 1.28e-3 for this one)
+    assert 5e-4 <= model.prefilter_tau <= 2.5e-2 and int(model.last_trace_counters[255]) == 0
     for k in ("points", "rgb_values", "sdf_output", "network_object_mask"):
         assert torch.equal(ref[k], out[k]), k
 
