@@ -94,6 +94,45 @@ def test_mlp_bitwise_deterministic():
             assert torch.equal(a, b) and torch.equal(fa, fb) and torch.equal(ga, gb)
 
 
+
+@pytest.mark.parametrize("preset,n", [("w512", 18944 + 37), ("w256", 40001), ("w512", 64 * 148 * 2)])
+def test_fused_head_matches_umma_head_and_is_position_independent(preset, n, monkeypatch):
+    """Exact SDF-only evaluations on the CTA-pair kernel compute the one-row head as an fp32 dot product in the last hidden
+    layer's epilogue (mlp_pair2_kernel.cuh, MlpArgs::fuse_head); MVSDF_FUSE_HEAD=0 keeps it an UMMA layer.  Both against the
+    fp64 oracle, against each other, and the fused path for independence of where a point sits (tile, column, CTA)."""
+    from mvsdf_b200 import ops
+    from tests.helpers import gate
+    dev = torch.device("cuda:0")
+    sd, sdf, rend = _nets(preset, dev)
+    gen = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=gen) * 2 - 1)
+    xd = x.to(dev)
+    monkeypatch.setenv("MVSDF_FUSE_HEAD", "0")
+    umma = ops.sdf_forward(sdf, xd, ops.HEAD_SDF_ONLY).clone()
+    monkeypatch.setenv("MVSDF_FUSE_HEAD", "1")
+    fused = ops.sdf_forward(sdf, xd, ops.HEAD_SDF_ONLY).clone()
+    assert torch.isfinite(fused).all()
+    idx = torch.randperm(n, generator=gen)[:4096]
+    with torch.no_grad():
+        ref64 = O.sdf_mlp(x[idx].double(), O.sdf_weights(sd, dtype=torch.float64))[:, 0]
+    gate(f"fused_head_vs_fp64[{preset}]", (fused.cpu()[idx].double() - ref64).abs().max().item(), TOL_SDF)
+    gate(f"umma_head_vs_fp64[{preset}]", (umma.cpu()[idx].double() - ref64).abs().max().item(), TOL_SDF)
+    gate(f"fused_vs_umma_head[{preset}]", (fused - umma).abs().max().item(), 1.5e-5)
+    # reversed and rotated point order: every point lands in another tile / column / CTA -- same bits
+    rev = ops.sdf_forward(sdf, xd.flip(0).contiguous(), ops.HEAD_SDF_ONLY).flip(0)
+    assert torch.equal(rev, fused), "fused head: a point's value depends on its position"
+    rot = ops.sdf_forward(sdf, torch.roll(xd, 77, 0).contiguous(), ops.HEAD_SDF_ONLY)
+    assert torch.equal(torch.roll(rot, -77, 0), fused)
+    # a device-side count (the tracer's request lists) takes the same path
+    n_dev = torch.tensor([n - 5], dtype=torch.int32, device=dev)
+    out = torch.full((n,), float("nan"), device=dev)
+    from mvsdf_b200 import _lib
+    _lib.check(_lib.lib().mvsdf_sdf_forward(sdf.handle, _lib.ptr(sdf.blob), _lib.ptr(xd), n, _lib.ptr(n_dev), ops.HEAD_SDF_ONLY,
+                                            _lib.ptr(out), None, ops._stream(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:n - 5], fused[:n - 5]) and torch.isnan(out[n - 5:]).all()
+
+
 def test_dense_grid_matches_oracle_on_a_subsample():
     """Row f3: the 3-D grid plots.py feeds to marching cubes, here 160^3 = 4.1 M points in one SDF-only launch;
     checked on a strided subsample against the fp64 oracle and for the grid's point ordering."""
