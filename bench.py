@@ -358,7 +358,7 @@ def run_ours(args):
                                      "sampler_rays_fraction": int(cnt[_lib.CTR_SAMPLER_RAYS]) / R,
                                      "minsdf_rays_fraction": int(cnt[_lib.CTR_MINSDF_RAYS]) / R,
                                      "guard_violations": violations, "exact_fallbacks": model.prefilter_fallbacks,
-                                     "note": "100-sample stages: screening pass (1 fp16 product, 5 chunks of 10-30 samples, stops behind "
+                                     "note": "100-sample stages: screening pass (1 fp16 product, 7 chunks of 2-30 samples, stops behind "
                                              "the first certainly negative sample) + exact pass (3 products) over the undecidable "
                                              "samples; outputs bit-identical to tau=0"}},
             "clocks": clk,

@@ -491,9 +491,11 @@ __device__ __forceinline__ void push_refine(const TraceCtx& c, int counter, int 
 // samples in chunks (chunk_begin) and drops a ray from the following chunks as soon as a chunk contains a value <= -tau;
 // samples never evaluated keep +inf, which every consumer treats as "certainly positive and not the minimum".  Rays
 // outside the true mask (training) and rays without a certain negative sample see all chunks.
-constexpr int kNumChunks = 5;
+constexpr int kNumChunks = 7;
 // chunk boundaries: sphere tracing leaves acc_start just in front of the surface, so most crossings sit in the first samples
-__host__ __device__ constexpr int chunk_begin(int c) { return c == 0 ? 0 : c == 1 ? 10 : c == 2 ? 20 : c == 3 ? 40 : c == 4 ? 70 : kSteps; }
+__host__ __device__ constexpr int chunk_begin(int c) {
+  return c == 0 ? 0 : c == 1 ? 2 : c == 2 ? 5 : c == 3 ? 10 : c == 4 ? 20 : c == 5 ? 40 : c == 6 ? 70 : kSteps;
+}
 constexpr int kChunkMax = 30;
 
 // points of chunk `chunk` of the active rays -> compact list (ref_pts, ref_src); act == nullptr: every ray of the batch

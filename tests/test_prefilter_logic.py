@@ -38,7 +38,7 @@ def candidates_sampler(lp, tau, inside_true):
     return want
 
 
-CHUNKS = (0, 10, 20, 40, 70, 100)        # chunk_begin() of csrc/tracer.cu
+CHUNKS = (0, 2, 5, 10, 20, 40, 70, 100)        # chunk_begin() of csrc/tracer.cu
 
 
 def chunked_screening(lp, tau, inside_true):
