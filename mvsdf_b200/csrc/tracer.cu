@@ -865,8 +865,13 @@ int mvsdf_trace(const mvsdf_net* net, const void* packed, const float* uv, const
   const int n_k = prm->line_step_iters;
   // worst case every ray overshoots at both ends: 2 R n_k candidates must fit the request list; MVSDF_SPEC_BACKOFF=0 forces
   // the sequential form (A/B)
-  static const bool spec_env = !(getenv("MVSDF_SPEC_BACKOFF") && atoi(getenv("MVSDF_SPEC_BACKOFF")) == 0);
-  const bool speculative = spec_env && 2ll * R * n_k <= c.cap;
+  // The speculative form trades evaluations for launches: it evaluates all n_k candidates of an overshooting ray where the
+  // walk uses 1-2 of them (measured at cfg2: +3.1 exact evaluations per ray, 576 vs 558 ms per step), and saves n_k - 1
+  // dependent launches per iteration (~50 us each: one tile's latency).  Break-even is near 1e5 rays; below 2^17 rays
+  // (every training batch, cfg1, cfg3) the launches dominate.  MVSDF_SPEC_BACKOFF=0 / =1 forces one form (A/B).
+  const char* spec_e = getenv("MVSDF_SPEC_BACKOFF");
+  const bool spec_fits = 2ll * R * n_k <= c.cap;
+  const bool speculative = spec_fits && (spec_e ? atoi(spec_e) != 0 : R <= (1ll << 17));
   int backoff_ctr = 0;      // E_trace slot of the previous iteration's back-off evaluations (filled by the next trace_top_kernel)
   for (int it = 0; it < prm->sphere_tracing_iters; ++it) {
     note_launch(); trace_top_kernel<<<grid_r, kBlock, 0, st>>>(c, it == 0, 0, ctr, n_k, backoff_ctr, mix_ctr);
