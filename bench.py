@@ -261,11 +261,14 @@ def run_ours(args):
     # what the kernels actually executed (the prefilter proves most sampler evaluations irrelevant and skips them):
     # exact evaluations = requests outside the 100-sample stages + refined samples + sdf_output; 3 fp16 products each
     sampled = 100 * (int(cnt[_lib.CTR_SAMPLER_RAYS]) + (int(cnt[_lib.CTR_MINSDF_RAYS]) if cfg["training"] and not args.skip_min_sdf else 0))
+    # sdf_output: the SDF-only launch covers the rays that are not surface rays; a surface ray's value comes out of the
+    # value + normal + feature pass (mvsdf_shade_rays), so it is not an execution of the kernel whose roofline this is
+    sdf_out_exec = R - n_hit
     if model.prefilter_tau > 0:
-        exact_exec = evals - sampled + refined + R
+        exact_exec = evals - sampled + refined + sdf_out_exec
         screen_exec = screened
     else:
-        exact_exec, screen_exec = evals + R, 0
+        exact_exec, screen_exec = evals + sdf_out_exec, 0
     exec_tflop = (3 * exact_exec + screen_exec) * fl["sdf_only"] / 1e12
     # roofline of the DOMINANT kernel = the exact SDF-only kernel (kind 0): algorithmic FLOPs of the evaluations its launches
     # really processed (the units one launch processes, not the evaluations the prefilter proved irrelevant)

@@ -155,7 +155,8 @@ int mvsdf_trace(const mvsdf_net* sdf_net, const void* sdf_packed, const float* u
  * get_rbg_value (:324-338): sdf_output for every ray, order-preserving gather of the surface rays, fused
  * value + analytic normal + feature pass, surface light field, scatter into rgb_values (ones where missed).
  *   surface_mask [R] uint8 (network_object_mask, AND object_mask in training);
- *   out_sdf [R] (optional), out_rgb_values [R,3], out_surf_pts / out_normals [R,3] (first M rows valid),
+ *   out_sdf [R] (optional; a surface ray's entry is the value column of the fused value + normal + feature pass, the other
+ *   rays go through one SDF-only launch over a compacted list), out_rgb_values [R,3], out_surf_pts / out_normals [R,3] (first M rows valid),
  *   out_surf_head [R,2] (optional: sdf and surface-indicator logit of the M surface points),
  *   out_hit_index [R] (ray index of each surface point), out_hit_offsets [B+1] (per-image exclusive offsets, [B] = M). */
 size_t mvsdf_shade_workspace_bytes(int64_t n_rays, int feature_size);

@@ -38,7 +38,7 @@ __global__ void hit_count_kernel(const uint8_t* __restrict__ mask, int R, int* _
 // single block: exclusive scan of block counts; also the per-image offsets (rays are image-major) and chunk counts
 __global__ void hit_scan_kernel(int* __restrict__ block_counts, int n_blocks, int n_images, int n_pixels,
                                 const uint8_t* __restrict__ mask, int* __restrict__ img_offsets,
-                                int* __restrict__ chunk_counts, int n_chunks) {
+                                int* __restrict__ chunk_counts, int n_chunks, int* __restrict__ miss_count) {
   __shared__ int carry;
   __shared__ int sh[1024];
   if (threadIdx.x == 0) carry = 0;
@@ -73,11 +73,13 @@ __global__ void hit_scan_kernel(int* __restrict__ block_counts, int n_blocks, in
   }
   for (int c = threadIdx.x; c < n_chunks; c += blockDim.x)
     chunk_counts[c] = min(max(carry - c * kHitChunk, 0), kHitChunk);
+  if (threadIdx.x == 0 && miss_count) *miss_count = n_images * n_pixels - carry;
 }
 
 __global__ void hit_scatter_kernel(const uint8_t* __restrict__ mask, int R, int n_pixels, const int* __restrict__ block_offsets,
                                    const float* __restrict__ points, const float* __restrict__ dirs,
-                                   int* __restrict__ hit_index, float* __restrict__ pts_hit, float* __restrict__ view_hit) {
+                                   int* __restrict__ hit_index, float* __restrict__ pts_hit, float* __restrict__ view_hit,
+                                   int* __restrict__ miss_index, float* __restrict__ pts_miss) {
   // one warp handles 32 consecutive rays at a time so that the order is preserved with ballots
   __shared__ int warp_base[kBlk / 32];
   __shared__ int sh_cnt[kBlk / 32];
@@ -113,6 +115,11 @@ __global__ void hit_scatter_kernel(const uint8_t* __restrict__ mask, int R, int 
         pts_hit[3 * (size_t)pos + k] = points[3 * (size_t)r + k];
         view_hit[3 * (size_t)pos + k] = -dirs[3 * (size_t)r + k];
       }
+    } else if (r < R && miss_index) {
+      const int pos = r - (out + __popc(bal & ((1u << lane) - 1)));      // rays before r minus surface rays before r
+      miss_index[pos] = r;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pts_miss[3 * (size_t)pos + k] = points[3 * (size_t)r + k];
     }
     out += __popc(bal);
   }
@@ -126,17 +133,24 @@ __global__ void fill_ones_kernel(float* __restrict__ p, long long n) {
 // rgb_values[surface_mask] = rgb (:301-304); also keeps (sdf, indicator) of the hit points
 __global__ void shade_scatter_kernel(const int* __restrict__ chunk_count, int begin, const int* __restrict__ hit_index,
                                      const float* __restrict__ rgb_hit, const float* __restrict__ full, int full_stride,
-                                     float* __restrict__ rgb_values, float* __restrict__ surf_head) {
+                                     float* __restrict__ rgb_values, float* __restrict__ surf_head, float* __restrict__ sdf_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *chunk_count) return;
   const int pos = begin + i;
   const int r = hit_index[pos];
+  if (sdf_out) sdf_out[r] = full[(size_t)i * full_stride];      // sdf_output of a surface ray: the value column of this pass
 #pragma unroll
   for (int k = 0; k < 3; ++k) rgb_values[3 * (size_t)r + k] = rgb_hit[3 * (size_t)pos + k];
   if (surf_head) {
     surf_head[2 * (size_t)pos] = full[(size_t)i * full_stride];
     surf_head[2 * (size_t)pos + 1] = full[(size_t)i * full_stride + 1];
   }
+}
+
+__global__ void miss_scatter_kernel(const int* __restrict__ miss_count, const int* __restrict__ miss_index,
+                                    const float* __restrict__ val, float* __restrict__ sdf_out) {
+  const int n = *miss_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdf_out[miss_index[i]] = val[i];
 }
 
 // ------------------------------------------------------------------ feature maps: NCHW -> channels-last
@@ -552,7 +566,7 @@ __global__ void set_double_kernel(double* p, double v) {
 }
 
 struct ShadeLayout {
-  size_t off_blocks, off_chunks, off_view, off_full, off_rgb, total;
+  size_t off_blocks, off_chunks, off_view, off_full, off_rgb, off_miss_pts, off_miss_idx, off_miss_val, off_miss_cnt, total;
   int n_blocks, n_chunks;
 };
 static ShadeLayout shade_layout(int64_t R, int feat) {
@@ -570,6 +584,10 @@ static ShadeLayout shade_layout(int64_t R, int feat) {
   l.off_view = take((size_t)R * 12);
   l.off_full = take((size_t)std::min<int64_t>(R, kHitChunk) * (feat + 2) * 4);
   l.off_rgb = take((size_t)R * 12);
+  l.off_miss_pts = take((size_t)R * 12);      // sdf_output of the rays that are not surface rays: compacted request list
+  l.off_miss_idx = take((size_t)R * 4);
+  l.off_miss_val = take((size_t)R * 4);
+  l.off_miss_cnt = take(4);
   l.total = off;
   return l;
 }
@@ -664,15 +682,23 @@ int mvsdf_shade_rays(const mvsdf_net* sdf_net, const void* sdf_packed, const mvs
   float* full = reinterpret_cast<float*>(ws + l.off_full);
   float* rgb_hit = reinterpret_cast<float*>(ws + l.off_rgb);
   int rc;
-  // sdf_output = implicit_network(points)[:, :1] for every ray (:202-203); only column 0 is ever read
-  if (out_sdf && (rc = mlp_sdf(sdf_net, sdf_packed, points, R, nullptr, MVSDF_HEAD_SDF_ONLY, out_sdf, nullptr, nullptr,
-                               false, st)))
-    return rc;
+  // sdf_output = implicit_network(points)[:, :1] for every ray (:202-203); only column 0 is ever read.  For a surface ray it
+  // is the value column of the value + normal + feature pass below (same point, same network: the reference evaluates it
+  // twice, :202 and :325), so the SDF-only launch covers the other rays only (43 % of them at cfg2).
+  int* miss_idx = reinterpret_cast<int*>(ws + l.off_miss_idx);
+  float* miss_pts = reinterpret_cast<float*>(ws + l.off_miss_pts);
+  float* miss_val = reinterpret_cast<float*>(ws + l.off_miss_val);
+  int* miss_cnt = reinterpret_cast<int*>(ws + l.off_miss_cnt);
   note_launch(); hit_count_kernel<<<l.n_blocks, kBlk, 0, st>>>(surface_mask, (int)R, block_counts);
   note_launch(); hit_scan_kernel<<<1, 1024, 0, st>>>(block_counts, l.n_blocks, n_images, n_pixels, surface_mask, out_hit_offsets,
-                                      chunk_counts, l.n_chunks);
+                                      chunk_counts, l.n_chunks, miss_cnt);
   note_launch(); hit_scatter_kernel<<<l.n_blocks, kBlk, 0, st>>>(surface_mask, (int)R, n_pixels, block_counts, points, ray_dirs,
-                                                  out_hit_index, out_surf_pts, view_hit);
+                                                  out_hit_index, out_surf_pts, view_hit, out_sdf ? miss_idx : nullptr, miss_pts);
+  if (out_sdf) {
+    if ((rc = mlp_sdf(sdf_net, sdf_packed, miss_pts, 0, miss_cnt, MVSDF_HEAD_SDF_ONLY, miss_val, nullptr, nullptr, false, st)))
+      return rc;
+    note_launch(); miss_scatter_kernel<<<sm_count() * 4, kBlk, 0, st>>>(miss_cnt, miss_idx, miss_val, out_sdf);
+  }
   note_launch(); fill_ones_kernel<<<(int)((3 * R + kBlk - 1) / kBlk), kBlk, 0, st>>>(out_rgb_values, 3 * R);
   const int stride = feature_size + 2;
   for (int c = 0; c < l.n_chunks; ++c) {
@@ -687,7 +713,7 @@ int mvsdf_shade_rays(const mvsdf_net* sdf_net, const void* sdf_packed, const mvs
     const int64_t cap = std::min<int64_t>(R - (int64_t)begin, kHitChunk);
     note_launch(); shade_scatter_kernel<<<(int)((cap + kBlk - 1) / kBlk), kBlk, 0, st>>>(chunk_counts + c, (int)begin, out_hit_index,
                                                                           rgb_hit, full, stride, out_rgb_values,
-                                                                          out_surf_head);
+                                                                          out_surf_head, out_sdf);
   }
   return check_cuda(cudaGetLastError(), "mvsdf_shade_rays launches");
 }
