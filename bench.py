@@ -85,7 +85,9 @@ class ClockSampler(threading.Thread):
     """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled in-process through NVML
     (nvidia_ml_py, initialised BEFORE the timed region): a fresh `nvidia-smi` process per sample initialises the driver's
     management library every time, which stalled kernel submission for 20-70 ms per sample (`value` 582 ms against 537 ms
-    in the un-sampled e2e loop of the same run).  Falls back to one nvidia-smi process per sample if NVML is unavailable."""
+    in the un-sampled e2e loop of the same run).  Falls back to one nvidia-smi process per sample if NVML is unavailable.
+    One sample per second: an NVML query while hundreds of per-launch CUDA events are outstanding (the roofline's timing)
+    costs ~9 ms on some boxes (measured: 572 ms at 4 Hz against 549 / 554 ms with either the sampler or the events off)."""
 
     def __init__(self, gpu_index: int, period: float = 1.0):
         super().__init__(daemon=True)
@@ -140,7 +142,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(self.period if self._nvml is None else min(self.period, 0.25))
+            self._stop_evt.wait(self.period)
 
     def stop(self):
         self._stop_evt.set()
